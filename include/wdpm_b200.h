@@ -76,8 +76,10 @@ typedef struct wdpm_config {
      * `rows` rows in total; see wdpm_stripe_* below. */
     int32_t stripe_row0;
     int32_t stripe_rows;
-    int32_t iters_per_launch; /* fused kernel: iterations carried per HBM round trip (0 = default 1) */
-    int32_t reserved[7];
+    int32_t iters_per_launch; /* fused kernel: iterations carried per HBM round trip (0 = default) */
+    int32_t fused_variant;    /* fused kernel tiling variant (0 = auto; see wdpm_fused_variant_info) */
+    int32_t fused_chunk_rows; /* owned rows per CTA, rounded up to a multiple of 3 (0 = auto) */
+    int32_t reserved[5];
 } wdpm_config;
 
 /* What one convergence block reports (src/WDPMCL.c:1239-1268). */
@@ -161,6 +163,9 @@ typedef struct wdpm_info {
     int32_t reserved[7];
 } wdpm_info;
 int wdpm_get_info(wdpm_solver *s, wdpm_info *info);
+/* Tiling of fused variant `variant` (1-based) for `dtype`; returns WDPM_E_ARG past the last one. */
+int wdpm_fused_variant_info(int32_t variant, int32_t dtype, int32_t *window_cols, int32_t *strip_cols,
+                            int32_t *iters_per_launch, int32_t *cta_threads, int32_t *smem_bytes);
 
 /* ---- row-stripe partition across GPUs (one solver per GPU) -----------------
  * Each stripe keeps halo rows of its neighbours' water. After every launch the

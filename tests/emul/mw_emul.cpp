@@ -1,0 +1,247 @@
+// TEST INFRASTRUCTURE - NOT PRODUCT CODE.
+//
+// CPU emulation of the fused kernel's schedule (wdpm_b200/csrc/kernels.cuh,
+// k_fused). It executes, CTA by CTA and step by step, exactly the loads, tile
+// relaxations and write-backs the CUDA kernel issues - using the SAME index
+// arithmetic (wdpm_b200/csrc/mw_schedule.h) and the SAME relax functions
+// (wdpm_b200/csrc/relax.cuh, compiled for the host) - on a model of the
+// shared-memory row ring. It exists so that halo widths, pipeline lags and ring
+// sizing can be proven against the oracle on a machine without a GPU, and it
+// checks the hazards a GPU run would only show as silent corruption:
+//   * every ring slot carries the id of the row it holds; a tile that finds a
+//     different row than it expects (slot reloaded too early, or not loaded yet)
+//     is an error;
+//   * a load into a slot whose write-back has not been retired by the
+//     corresponding bulk wait is an error (loads are modelled as landing
+//     immediately, stores as reading as late as the kernel allows).
+// Nothing under wdpm_b200/ links against this file.
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <vector>
+
+#include "../../wdpm_b200/csrc/mw_schedule.h"
+#include "../../wdpm_b200/csrc/relax.cuh"
+
+using namespace wdpm;
+
+namespace {
+
+struct Layout {
+    int R, C, pitch, nrows_dev;
+    size_t at(int i, int j) const { return (size_t)(i + kPadTop) * pitch + (size_t)(j + kPadLeft); }
+};
+
+template <typename T>
+struct Event { T w_outlet, w_centre; int valid; };
+
+struct Errors {
+    long long wrong_row = 0;      // tile touched a slot holding another row
+    long long load_over_store = 0;  // load landed in a slot with an unretired store
+    long long double_store = 0;
+    long long unstored = 0;
+};
+
+template <typename T, int MODULE, typename CFG>
+void run_cta(const Layout& L, const T* w_in, T* w_out, const T* dem, T nodata, int strip, int chunk,
+             int chunk_triples, int total_triples, int drainrow, int draincol, Event<T>* events, Errors& err,
+             std::vector<unsigned char>& stored_mask) {
+    constexpr int W = CFG::W, NT = CFG::NT, NPH = CFG::NPH, NRING = CFG::NRING, PF = CFG::PF;
+    MwTile<CFG> tile;
+    tile.init(strip, chunk, chunk_triples, total_triples);
+    std::vector<T> ring_w((size_t)NRING * W), ring_d((size_t)NRING * W);
+    std::vector<int> slot_row(NRING, INT32_MIN);
+    // store groups in flight: each is a list of slots
+    std::deque<std::vector<int>> groups;
+    std::vector<int> slot_pending(NRING, 0);
+    const int col0 = tile.x0 + kPadLeft;
+
+    auto issue_loads = [&](int s) {
+        for (int t = 0; t < NT; t++) {
+            const int m = tile.triple(s, 0, t);
+            if (!tile.staged(m)) continue;
+            for (int k = 0; k < 3; k++) {
+                const int row = 3 * m + k;
+                const int slot = tile.ring_slot(row);
+                if (slot_pending[slot]) err.load_over_store++;
+                const size_t src = (size_t)(row + kPadTop) * L.pitch + col0;
+                std::memcpy(&ring_w[(size_t)slot * W], w_in + src, W * sizeof(T));
+                std::memcpy(&ring_d[(size_t)slot * W], dem + src, W * sizeof(T));
+                slot_row[slot] = row;
+            }
+        }
+    };
+    auto wait_read = [&](size_t allowed) {
+        while (groups.size() > allowed) {
+            for (int slot : groups.front()) slot_pending[slot]--;
+            groups.pop_front();
+        }
+    };
+
+    for (int s = 0; s < PF && s < tile.n_steps; s++) issue_loads(s);
+    for (int s = 0; s < tile.n_steps; s++) {
+        if (s + PF < tile.n_steps) issue_loads(s + PF);
+        for (int cofs = 0; cofs < 3; cofs++) {
+            constexpr int nc = CFG::NC;
+            for (int item = 0; item < NPH * NT * nc; item++) {
+                const int c = item % nc, pt = item / nc, t = pt % NT, ph = pt / NT, q = ph % 3;
+                const int m = tile.triple(s, ph, t);
+                if (!tile.runnable(m, q)) continue;
+                const int row0 = 3 * m + q;
+                int s0 = tile.ring_slot(row0);
+                int s1 = s0 + 1; if (s1 == NRING) s1 = 0;
+                int s2 = s1 + 1; if (s2 == NRING) s2 = 0;
+                if (slot_row[s0] != row0 || slot_row[s1] != row0 + 1 || slot_row[s2] != row0 + 2) err.wrong_row++;
+                const int j = 3 * c + cofs + 1;
+                T* w0 = &ring_w[(size_t)s0 * W]; T* w1 = &ring_w[(size_t)s1 * W]; T* w2 = &ring_w[(size_t)s2 * W];
+                const T* d0 = &ring_d[(size_t)s0 * W]; const T* d1 = &ring_d[(size_t)s1 * W]; const T* d2 = &ring_d[(size_t)s2 * W];
+                if (MODULE == kDrain) {
+                    const int crow = row0 + 1, ccol = tile.x0 + j;
+                    const int orow = drainrow - crow, ocol = draincol - ccol;
+                    if (orow >= -1 && orow <= 1 && ocol >= -1 && ocol <= 1) {
+                        if (orow == 0 && ocol == 0) continue;
+                        T evo, evc; bool drained;
+                        relax_tile_at_outlet<T>(w0, w1, w2, d0, d1, d2, j, nodata, orow, ocol, &evo, &evc, &drained);
+                        if (drained && tile.owns_row(crow) && tile.owns_col(ccol)) {
+                            Event<T>& e = events[(ph / 3) * 9 + q * 3 + cofs];
+                            e.w_outlet = evo; e.w_centre = evc; e.valid = 1;
+                        }
+                        continue;
+                    }
+                }
+                relax_tile<T, MODULE>(w0, w1, w2, d0, d1, d2, j, nodata);
+            }
+        }
+        std::vector<int> grp;
+        for (int t = 0; t < NT; t++) {
+            const int m = tile.triple(s, NPH - 1, t);
+            for (int k = 0; k < 3; k++) {
+                const int row = 3 * m + 2 + k;
+                if (!tile.owns_row(row)) continue;
+                const int slot = tile.ring_slot(row);
+                if (slot_row[slot] != row) err.wrong_row++;
+                const size_t dst = (size_t)(row + kPadTop) * L.pitch + col0 + CFG::HL;
+                std::memcpy(w_out + dst, &ring_w[(size_t)slot * W + CFG::HL], CFG::TWV * sizeof(T));
+                for (int c = 0; c < CFG::TWV; c++) {
+                    if (stored_mask[dst + c]) err.double_store++;
+                    stored_mask[dst + c] = 1;
+                }
+                grp.push_back(slot);
+                slot_pending[slot]++;
+            }
+        }
+        if (!grp.empty()) groups.push_back(grp);
+        wait_read(1);
+    }
+    wait_read(0);
+}
+
+template <typename T, int MODULE, typename CFG>
+int run_launches(T* w_padded, const T* d_padded, int R, int C, T nodata, int n_launches, int chunk_triples,
+                 int drainrow, int draincol, T* totaldrain, long long* err_out) {
+    Layout L;
+    L.R = R; L.C = C;
+    const int n_strips = (C + 2 + CFG::TWV - 1) / CFG::TWV;
+    const int total_triples = (R + 2 + 2) / 3;
+    L.pitch = ((kPadLeft + n_strips * CFG::TWV + (CFG::W - CFG::TWV - CFG::HL) + 31) / 32) * 32;
+    L.nrows_dev = kPadTop + 3 * (total_triples + 2 * CFG::K) + 3;
+    if (chunk_triples <= 0) chunk_triples = total_triples;
+    const int n_chunks = (total_triples + chunk_triples - 1) / chunk_triples;
+    const size_t n = (size_t)L.pitch * L.nrows_dev;
+    std::vector<T> dem(n, nodata), wa(n, T(0)), wb(n, T(0));
+    for (int i = 0; i < R + 2; i++)
+        for (int j = 0; j < C + 2; j++) {
+            dem[L.at(i, j)] = d_padded[(size_t)i * (C + 2) + j];
+            wa[L.at(i, j)] = w_padded[(size_t)i * (C + 2) + j];
+        }
+    Errors err;
+    T* cur = wa.data();
+    T* nxt = wb.data();
+    T td = *totaldrain;
+    for (int l = 0; l < n_launches; l++) {
+        std::vector<Event<T>> events(9 * CFG::K, Event<T>{T(0), T(0), 0});
+        std::vector<unsigned char> stored(n, 0);
+        for (int chunk = 0; chunk < n_chunks; chunk++)
+            for (int strip = 0; strip < n_strips; strip++)
+                run_cta<T, MODULE, CFG>(L, cur, nxt, dem.data(), nodata, strip, chunk, chunk_triples, total_triples,
+                                        drainrow, draincol, events.data(), err, stored);
+        for (int i = 0; i < R + 2; i++)
+            for (int j = 0; j < C + 2; j++)
+                if (!stored[L.at(i, j)]) err.unstored++;
+        for (auto& e : events)
+            if (e.valid) { td = td + e.w_outlet; td = td + e.w_centre; }
+        T* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    // margins of the final buffer must still be zero
+    long long margin_dirty = 0;
+    {
+        std::vector<unsigned char> inside(n, 0);
+        for (int i = 0; i < R + 2; i++)
+            for (int j = 0; j < C + 2; j++) inside[L.at(i, j)] = 1;
+        for (size_t k = 0; k < n; k++)
+            if (!inside[k] && cur[k] != T(0)) margin_dirty++;
+    }
+    for (int i = 0; i < R + 2; i++)
+        for (int j = 0; j < C + 2; j++) w_padded[(size_t)i * (C + 2) + j] = cur[L.at(i, j)];
+    *totaldrain = td;
+    err_out[0] = err.wrong_row;
+    err_out[1] = err.load_over_store;
+    err_out[2] = err.double_store;
+    err_out[3] = err.unstored;
+    err_out[4] = margin_dirty;
+    return 0;
+}
+
+template <typename T, typename CFG>
+int dispatch_module(int module, T* w, const T* d, int R, int C, T nodata, int n, int ct, int dr, int dc, T* td, long long* e) {
+    switch (module) {
+        case kAdd: return run_launches<T, kAdd, CFG>(w, d, R, C, nodata, n, ct, dr, dc, td, e);
+        case kSubtract: return run_launches<T, kSubtract, CFG>(w, d, R, C, nodata, n, ct, dr, dc, td, e);
+        case kDrain: return run_launches<T, kDrain, CFG>(w, d, R, C, nodata, n, ct, dr, dc, td, e);
+    }
+    return -1;
+}
+
+template <typename T>
+int dispatch_cfg(int cfg, int module, T* w, const T* d, int R, int C, T nodata, int n, int ct, int dr, int dc, T* td, long long* e) {
+    switch (cfg) {
+        case 0: return dispatch_module<T, MwCfg<512, 1, 1, 2>>(module, w, d, R, C, nodata, n, ct, dr, dc, td, e);
+        case 1: return dispatch_module<T, MwCfg<64, 1, 1, 1>>(module, w, d, R, C, nodata, n, ct, dr, dc, td, e);
+        case 2: return dispatch_module<T, MwCfg<64, 1, 1, 2>>(module, w, d, R, C, nodata, n, ct, dr, dc, td, e);
+        case 3: return dispatch_module<T, MwCfg<96, 2, 1, 1>>(module, w, d, R, C, nodata, n, ct, dr, dc, td, e);
+        case 4: return dispatch_module<T, MwCfg<128, 1, 2, 2>>(module, w, d, R, C, nodata, n, ct, dr, dc, td, e);
+        case 5: return dispatch_module<T, MwCfg<128, 2, 2, 1>>(module, w, d, R, C, nodata, n, ct, dr, dc, td, e);
+        case 6: return dispatch_module<T, MwCfg<256, 1, 4, 3>>(module, w, d, R, C, nodata, n, ct, dr, dc, td, e);
+        case 7: return dispatch_module<T, MwCfg<384, 2, 1, 2>>(module, w, d, R, C, nodata, n, ct, dr, dc, td, e);
+    }
+    return -2;
+}
+
+template <typename CFG>
+static int cfg_info(int* W, int* TWV, int* K, int* NRING) { *W = CFG::W; *TWV = CFG::TWV; *K = CFG::K; *NRING = CFG::NRING; return 0; }
+}  // namespace
+
+extern "C" {
+int mw_emul_cfg_info(int cfg, int* W, int* TWV, int* K, int* NRING) {
+    switch (cfg) {
+        case 0: return cfg_info<MwCfg<512, 1, 1, 2>>(W, TWV, K, NRING);
+        case 1: return cfg_info<MwCfg<64, 1, 1, 1>>(W, TWV, K, NRING);
+        case 2: return cfg_info<MwCfg<64, 1, 1, 2>>(W, TWV, K, NRING);
+        case 3: return cfg_info<MwCfg<96, 2, 1, 1>>(W, TWV, K, NRING);
+        case 4: return cfg_info<MwCfg<128, 1, 2, 2>>(W, TWV, K, NRING);
+        case 5: return cfg_info<MwCfg<128, 2, 2, 1>>(W, TWV, K, NRING);
+        case 6: return cfg_info<MwCfg<256, 1, 4, 3>>(W, TWV, K, NRING);
+        case 7: return cfg_info<MwCfg<384, 2, 1, 2>>(W, TWV, K, NRING);
+    }
+    return -1;
+}
+int mw_emul_run_f64(int cfg, int module, double* w, const double* d, int R, int C, double nodata, int n_launches,
+                    int chunk_triples, int drainrow, int draincol, double* totaldrain, long long* errors5) {
+    return dispatch_cfg<double>(cfg, module, w, d, R, C, nodata, n_launches, chunk_triples, drainrow, draincol, totaldrain, errors5);
+}
+int mw_emul_run_f32(int cfg, int module, float* w, const float* d, int R, int C, float nodata, int n_launches,
+                    int chunk_triples, int drainrow, int draincol, float* totaldrain, long long* errors5) {
+    return dispatch_cfg<float>(cfg, module, w, d, R, C, nodata, n_launches, chunk_triples, drainrow, draincol, totaldrain, errors5);
+}
+}

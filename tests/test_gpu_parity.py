@@ -1,0 +1,239 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle - bit for bit."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_text, random_case
+from oracle import pyoracle as po
+from wdpm_b200 import ascgrid
+
+pytestmark = pytest.mark.gpu
+
+MODS = [("add", 0), ("subtract", 1), ("drain", 2)]
+NODATA = -99999.0
+
+
+def _solver(cuda_lib, D, W, module, dtype, **kw):
+    from wdpm_b200 import F32, F64, Solver
+    s = Solver(D.shape[0] - 2, D.shape[1] - 2, NODATA, module, dtype=F64 if dtype == np.float64 else F32, **kw)
+    s.upload(D[1:-1, 1:-1], W[1:-1, 1:-1])
+    return s
+
+
+def _cuda_iterate(cuda_lib, D, W, module, dtype, n, outlet=None, td=0.0, **kw):
+    s = _solver(cuda_lib, D, W, module, dtype, **kw)
+    if module == 2:
+        s.set_outlet(*outlet)
+        s.set_total_drain(td)
+    s.iterate(n)
+    out = s.download_water()
+    tdo = s.get_total_drain()
+    info = s.info()
+    s.close()
+    return ascgrid.pad_grid(out, dtype(0)), tdo, info
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("mn,mod", MODS)
+def test_colour_kernel_matches_oracle(cuda_lib, oracle, dt, mn, mod):
+    from wdpm_b200 import KERNEL_COLOUR
+    rng = np.random.default_rng(21)
+    for rows, cols in ((1, 1), (2, 7), (33, 65), (100, 131), (257, 190)):
+        D, W = random_case(rng, rows, cols, dt)
+        outlet = oracle.find_outlet(D) or (1, 1)
+        a = W.copy()
+        ta = oracle.iterate(a, D, NODATA, mod, 25, outlet=outlet, totaldrain=0.5)
+        b, tb, _ = _cuda_iterate(cuda_lib, D, W, mod, dt, 25, outlet=outlet, td=0.5, kernel=KERNEL_COLOUR)
+        assert np.array_equal(a, b), (rows, cols)
+        if mod == 2:
+            assert dt(ta) == dt(tb)
+
+
+def _variants(dtype_code):
+    from wdpm_b200 import solver
+    v, out = 1, []
+    while solver.fused_variant_info(v, dtype_code) is not None:
+        out.append(v)
+        v += 1
+    return out
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("mn,mod", MODS)
+def test_fused_kernel_matches_oracle_all_variants(cuda_lib, oracle, dt, mn, mod):
+    """Every tiling variant (window width, triples per step, iterations per launch), several chunkings."""
+    from wdpm_b200 import F32, F64, KERNEL_FUSED, solver
+    code = F64 if dt == np.float64 else F32
+    rng = np.random.default_rng(31)
+    for variant in _variants(code):
+        K = solver.fused_variant_info(variant, code)["iters_per_launch"]
+        for rows, cols, chunk_rows in ((50, 70, 0), (61, 130, 15), (97, 700, 21), (1, 1, 0), (200, 45, 48)):
+            D, W = random_case(rng, rows, cols, dt)
+            outlet = oracle.find_outlet(D) or (1, 1)
+            n = 3 * K + (1 if K > 1 else 0)  # also exercise the remainder path
+            a = W.copy()
+            ta = oracle.iterate(a, D, NODATA, mod, n, outlet=outlet, totaldrain=0.25)
+            b, tb, info = _cuda_iterate(cuda_lib, D, W, mod, dt, n, outlet=outlet, td=0.25, kernel=KERNEL_FUSED,
+                                        fused_variant=variant, fused_chunk_rows=chunk_rows)
+            assert info["kernel"] == KERNEL_FUSED
+            assert np.array_equal(a, b), (variant, rows, cols, chunk_rows, int((a != b).sum()))
+            if mod == 2:
+                assert dt(ta) == dt(tb), (variant, rows, cols)
+
+
+def test_fused_drain_outlet_on_ownership_boundaries(cuda_lib, oracle):
+    from wdpm_b200 import F64, KERNEL_FUSED, solver
+    twv = solver.fused_variant_info(2, F64)["strip_cols"]
+    rng = np.random.default_rng(9)
+    for orow, ocol in ((15, twv), (15, twv - 1), (16, twv + 1), (14, 2 * twv), (1, 1), (30, 60)):
+        D, W = random_case(rng, 30, 60, np.float64, nodata_fraction=0.0, wet_fraction=1.0)
+        a = W.copy()
+        ta = oracle.iterate(a, D, NODATA, po.DRAIN, 4, outlet=(orow, ocol), totaldrain=1.0)
+        b, tb, _ = _cuda_iterate(cuda_lib, D, W, 2, np.float64, 4, outlet=(orow, ocol), td=1.0, kernel=KERNEL_FUSED,
+                                 fused_variant=2, fused_chunk_rows=15)
+        assert np.array_equal(a, b) and ta == tb, (orow, ocol)
+
+
+@pytest.mark.parametrize("dn,dt", [("f64", np.float64), ("f32", np.float32)])
+@pytest.mark.parametrize("mn,mod", MODS)
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_golden_vectors_from_verbatim_kernel(cuda_lib, dn, dt, mn, mod, kernel):
+    """tests/golden/crop_vectors.npz was produced by the verbatim runoff.cl in the build container."""
+    g = np.load(GOLDEN / "crop_vectors.npz")
+    D = ascgrid.pad_grid(g["dem"].astype(dt), dt(g["nodata"]))
+    W = g[f"w0_{dn}"]
+    b, tb, _ = _cuda_iterate(cuda_lib, D, W, mod, dt, int(g["iters"]), outlet=tuple(int(x) for x in g["outlet"]), td=0.0,
+                             kernel=kernel, fused_variant=2 if kernel == 2 else 0, fused_chunk_rows=24)
+    assert np.array_equal(b, g[f"w_{mn}_{dn}"])
+    if mod == 2:
+        assert dt(tb) == g[f"td_{mn}_{dn}"]
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_run_block_matches_oracle_block(cuda_lib, oracle, dt, kernel):
+    """Threshold + snapshot + iterations + masked max-diff / sum / totaldrain (WDPMCL.c:1055-1268)."""
+    from wdpm_b200 import F32, F64, Solver
+    rng = np.random.default_rng(41)
+    for mod in (0, 1, 2):
+        D, W = random_case(rng, 120, 150, dt, depth=0.02)
+        W[5:20, 5:20] = dt(-99999.0)  # water files carry NODATA values; the threshold pass must clear them
+        outlet = oracle.find_outlet(D)
+        thres = 0.004
+        a = W.copy()
+        td = 0.125
+        s = Solver(120, 150, NODATA, mod, dtype=F64 if dt == np.float64 else F32, zero_threshold=thres, kernel=kernel,
+                   fused_variant=2 if kernel == 2 else 0, fused_chunk_rows=30)
+        s.upload(D[1:-1, 1:-1], W[1:-1, 1:-1])
+        if mod == 2:
+            s.set_outlet(*outlet)
+            s.set_total_drain(td)
+        for _ in range(2):
+            md, ms, td = oracle.block(a, D, NODATA, mod, dt(thres), 30, outlet=outlet, totaldrain=td)
+            r = s.run_block(30)
+            assert r.max_diff == md
+            assert abs(r.masked_sum - ms) <= 1e-12 * abs(ms)
+            if mod == 2:
+                assert dt(r.total_drain) == dt(td)
+            assert r.wet_cells == int(np.count_nonzero((a > 0) & (D > NODATA)))
+        assert np.array_equal(ascgrid.pad_grid(s.download_water(), dt(0)), a)
+        s.close()
+
+
+def test_initial_conditions_and_outlet(cuda_lib, oracle):
+    from oracle_backend import OracleBackend
+    from wdpm_b200 import F64, Solver
+    rng = np.random.default_rng(51)
+    D, W = random_case(rng, 90, 110, np.float64, depth=0.05)
+    dem, w = D[1:-1, 1:-1], W[1:-1, 1:-1]
+    for what in ("add", "subtract"):
+        s = Solver(90, 110, NODATA, 0, dtype=F64)
+        s.upload(dem, w)
+        ob = OracleBackend(90, 110, NODATA, 0, 0.0)
+        ob.upload(dem, w)
+        if what == "add":
+            s.apply_add(0.3, 0.8)
+            ob.apply_add(0.3, 0.8)
+        else:
+            s.apply_subtract(0.02)
+            ob.apply_subtract(0.02)
+        assert np.array_equal(s.download_water(), ob.download_water())
+        r, c, e = s.find_outlet()
+        assert (r, c) == oracle.find_outlet(D) and e == D[r, c]
+        assert s.get_cell_water(r, c) == ob.get_cell_water(r, c)
+        s.close()
+
+
+def test_basin5_validation_sequence_on_gpu(cuda_lib, basin5, tmp_path):
+    """BASELINE.json configs[1] and validate_WDPM.sh: Add 10 mm -> Drain -> Subtract 10 mm on basin5,
+    through the CUDA solver; output files must equal the unmodified reference's OpenCL-branch files."""
+    from test_oracle import _check_goldens
+    from wdpm_b200.wdpmcl import ModuleParams, default_backend, run_module
+    hdr, dem = basin5
+    steps = [
+        ("add10", ModuleParams("add", depth_mm=10, runoff_fraction=1.0, elevation_tol_mm=1.0, zero_threshold_mm=0.005), 30000),
+        ("drain", ModuleParams("drain", elevation_tol_mm=0.1, drain_tol_m3=1.0, zero_threshold_mm=0.005), 11000),
+        ("sub10", ModuleParams("subtract", depth_mm=10, elevation_tol_mm=1.0, zero_threshold_mm=0.005), 1000),
+    ]
+    water = None
+    for name, params, iters in steps:
+        rep = run_module(dem, hdr.nodata, hdr.cellsize, params, water=water, backend=default_backend())
+        assert rep.iterations == iters
+        path = tmp_path / f"{name}.asc"
+        ascgrid.write_asc(path, hdr, rep.water)
+        text = path.read_text()
+        assert text == golden_text(f"ref_opencl_{name}.asc.gz"), name
+        _check_goldens(name, text)
+        _, water = ascgrid.read_asc(path)
+
+
+def test_basin5_fused_kernel_equals_colour_kernel(cuda_lib, basin5):
+    """Same DEM through both kernels for two blocks of Add: identical grids and reductions."""
+    from wdpm_b200 import F64, KERNEL_COLOUR, KERNEL_FUSED, Solver
+    hdr, dem = basin5
+    res = []
+    for kernel, variant in ((KERNEL_COLOUR, 0), (KERNEL_FUSED, 1), (KERNEL_FUSED, 5), (KERNEL_FUSED, 6)):
+        s = Solver(hdr.nrows, hdr.ncols, hdr.nodata, 0, dtype=F64, zero_threshold=5e-6, kernel=kernel, fused_variant=variant)
+        s.upload(dem, None)
+        s.apply_add(0.3, 1.0)
+        r = [s.run_block(200) for _ in range(2)]
+        res.append((s.download_water(), [(x.max_diff, x.masked_sum, x.wet_cells) for x in r]))
+        s.close()
+    for w, r in res[1:]:
+        assert np.array_equal(w, res[0][0])
+        assert r == res[0][1]
+
+
+@pytest.mark.parametrize("dt,size", [(np.float32, 8192), (np.float64, 4096)])
+def test_large_grid_properties(cuda_lib, dt, size):
+    """Sizes the oracle cannot reach in seconds: the fused kernel must equal the colour kernel bit for
+    bit (two independent CUDA code paths), conserve mass to rounding, keep margins dry and be a no-op
+    on a dry grid. Also checks an oracle-computed crop far from the crop's edges."""
+    import torch
+    from oracle import pyoracle
+    from wdpm_b200 import F32, F64, KERNEL_COLOUR, KERNEL_FUSED, Solver, synth
+    code = F64 if dt == np.float64 else F32
+    dem = synth.fractal_dem(size, size, seed=size, device="cuda", dtype=torch.float64)
+    dem = (dem - dem.min()).to(torch.float32 if dt == np.float32 else torch.float64).cpu().numpy()
+    n_it = 6
+    outs = []
+    for kernel in (KERNEL_COLOUR, KERNEL_FUSED):
+        s = Solver(size, size, NODATA, 0, dtype=code, kernel=kernel)
+        s.upload(dem, None)
+        s.apply_add(0.1, 1.0)
+        s.iterate(n_it)
+        outs.append(s.download_water())
+        if kernel == KERNEL_FUSED:
+            s.upload_water(None)          # dry grid: nothing may change
+            s.iterate(2)
+            assert not s.download_water().any()
+        s.close()
+    assert np.array_equal(outs[0], outs[1])
+    total = outs[1].astype(np.float64).sum()
+    assert abs(total - 0.1 * size * size) / (0.1 * size * size) < (1e-12 if dt == np.float64 else 2e-6)
+    # oracle on a crop: cells further than 3*n_it+3 from the crop edge cannot see the cut
+    r0, c0, n = size // 2 - 100, size // 3, 256
+    D = ascgrid.pad_grid(dem[r0:r0 + n, c0:c0 + n], dt(NODATA))
+    W = np.where(D > NODATA, dt(0.1), dt(0)).astype(dt)
+    pyoracle.Oracle().iterate(W, D, NODATA, 0, n_it)
+    m = 3 * n_it + 3
+    assert np.array_equal(W[1 + m:-1 - m, 1 + m:-1 - m], outs[1][r0 + m:r0 + n - m, c0 + m:c0 + n - m])

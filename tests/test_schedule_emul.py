@@ -1,0 +1,102 @@
+"""CPU: the fused kernel's schedule (wdpm_b200/csrc/mw_schedule.h) proven against the oracle.
+
+tests/emul/mw_emul.cpp executes the CUDA kernel's exact sequence of bulk loads, tile relaxations
+and write-backs on a model of the shared-memory row ring, with the kernel's own index arithmetic and
+relax functions compiled for the host. Bit-equality with the oracle shows the halo widths, phase lags
+and multi-iteration pipelining are right; its hazard counters show the ring is large enough."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import random_case
+from oracle import pyoracle as po
+
+HERE = Path(__file__).resolve().parent
+SRC = HERE / "emul" / "mw_emul.cpp"
+NCFG = 8
+
+
+def _build(extra=(), name="libmw_emul.so"):
+    out = HERE / "emul" / "_build" / name
+    out.parent.mkdir(exist_ok=True)
+    deps = [SRC, HERE.parent / "wdpm_b200" / "csrc" / "mw_schedule.h", HERE.parent / "wdpm_b200" / "csrc" / "relax.cuh"]
+    if not out.exists() or any(d.stat().st_mtime > out.stat().st_mtime for d in deps):
+        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
+                        *extra, str(SRC), "-o", str(out)], check=True)
+    return C.CDLL(str(out))
+
+
+@pytest.fixture(scope="module")
+def emul():
+    return _build()
+
+
+def run_emul(lib, cfg, module, w, d, nodata, n_launches, chunk_triples, outlet=(-10, -10), td=0.0):
+    sfx, ct = ("_f64", C.c_double) if w.dtype == np.float64 else ("_f32", C.c_float)
+    R, Cc = w.shape[0] - 2, w.shape[1] - 2
+    tdv = np.array([td], dtype=w.dtype)
+    err = np.zeros(5, dtype=np.int64)
+    rc = getattr(lib, "mw_emul_run" + sfx)(cfg, module, w.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), R, Cc,
+                                          ct(nodata), n_launches, chunk_triples, outlet[0], outlet[1],
+                                          tdv.ctypes.data_as(C.c_void_p), err.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return float(tdv[0]), err
+
+
+def cfg_info(lib, cfg):
+    a = [C.c_int() for _ in range(4)]
+    lib.mw_emul_cfg_info(cfg, *[C.byref(x) for x in a])
+    return dict(zip(("W", "TWV", "K", "NRING"), (x.value for x in a)))
+
+
+@pytest.mark.parametrize("cfg", range(1, NCFG))
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_schedule_is_bit_exact(oracle, emul, cfg, dt):
+    K = cfg_info(emul, cfg)["K"]
+    rng = np.random.default_rng(100 + cfg)
+    for rows, cols, chunk_triples in ((50, 70, 0), (61, 130, 5), (97, 45, 7), (1, 1, 0), (3, 200, 1)):
+        for mod in (po.ADD, po.SUBTRACT, po.DRAIN):
+            D, W = random_case(rng, rows, cols, dt)
+            outlet = (oracle.find_outlet(D) or (1, 1)) if mod == po.DRAIN else (-10, -10)
+            a, b = W.copy(), W.copy()
+            ta = oracle.iterate(a, D, -99999.0, mod, 3 * K, outlet=outlet if mod == po.DRAIN else (0, 0), totaldrain=0.25)
+            tb, err = run_emul(emul, cfg, mod, b, D, -99999.0, 3, chunk_triples, outlet, 0.25)
+            assert not err.any(), (cfg, rows, cols, mod, err)
+            assert np.array_equal(a, b), (cfg, rows, cols, mod)
+            assert ta == tb
+
+
+def test_production_window_one_iteration(oracle, emul):
+    """cfg 0 = the 512-column production window, on a grid wider than one strip."""
+    rng = np.random.default_rng(7)
+    D, W = random_case(rng, 40, 1100, np.float64)
+    a, b = W.copy(), W.copy()
+    oracle.iterate(a, D, -99999.0, po.ADD, 2)
+    _, err = run_emul(emul, 0, po.ADD, b, D, -99999.0, 2, 6)
+    assert not err.any() and np.array_equal(a, b)
+
+
+def test_drain_outlet_on_ownership_boundaries(oracle, emul):
+    """The outlet's neighbours straddle strips and chunks: events must still fold in sub-pass order."""
+    rng = np.random.default_rng(9)
+    info = cfg_info(emul, 1)
+    twv = info["TWV"]
+    for orow, ocol in ((15, twv), (15, twv - 1), (16, twv + 1), (14, 2 * twv), (1, 1), (30, 60)):
+        D, W = random_case(rng, 30, 60, np.float64, nodata_fraction=0.0, wet_fraction=1.0)
+        a, b = W.copy(), W.copy()
+        ta = oracle.iterate(a, D, -99999.0, po.DRAIN, 4, outlet=(orow, ocol), totaldrain=1.0)
+        tb, err = run_emul(emul, 1, po.DRAIN, b, D, -99999.0, 4, 5, (orow, ocol), 1.0)
+        assert not err.any() and np.array_equal(a, b) and ta == tb, (orow, ocol)
+
+
+def test_hazard_checks_fire_when_ring_is_too_small():
+    """Negative control: with three ring rows fewer the emulator must report a load landing on
+    rows whose write-back is still in flight."""
+    lib = _build(extra=("-DWDPM_NRING_DELTA=-3",), name="libmw_emul_shrunk.so")
+    rng = np.random.default_rng(5)
+    D, W = random_case(rng, 50, 70, np.float64)
+    _, err = run_emul(lib, 7, po.ADD, W.copy(), D, -99999.0, 1, 0)
+    assert err[0] > 0 or err[1] > 0

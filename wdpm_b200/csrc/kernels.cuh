@@ -1,0 +1,479 @@
+// CUDA kernels of the WDPM redistribution solver (sm_100a).
+//
+// Device layout: every grid (dem, water ping, water pong, block-start snapshot)
+// is a row-major array of `nrows_dev` x `pitch` elements. Padded grid cell
+// (i, j) - the reference's bigdem[i][j] / bigwater[i][j], i in [0,R+1],
+// j in [0,C+1] (src/WDPMCL.c:795-807) - lives at
+//     (i + kPadTop) * pitch + (j + kPadLeft).
+// Everything outside the (R+2)x(C+2) padded grid is margin: dem = nodata,
+// water = 0. A margin cell can never become a centre (dry) nor receive water
+// (invalid neighbour), so kernels may compute on margins freely; this replaces
+// the reference's row/col range guard (src/runoff.cl:145).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "mw_schedule.h"
+#include "relax.cuh"
+
+namespace wdpm {
+
+struct Geom {
+    int R, C;          // interior rows / cols held by this solver
+    int pitch;         // elements per device row (multiple of 32)
+    int nrows_dev;     // device rows
+    long long cells_dev() const { return (long long)pitch * nrows_dev; }
+};
+
+__device__ __forceinline__ size_t dev_index(const Geom& g, int i, int j) {
+    return (size_t)(i + kPadTop) * (size_t)g.pitch + (size_t)(j + kPadLeft);
+}
+
+// ---------------------------------------------------------------------------
+// Elementwise helpers
+// ---------------------------------------------------------------------------
+
+template <typename T>
+__global__ void k_fill(T* __restrict__ a, long long n, T v) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        a[i] = v;
+}
+
+// Copy an unpadded device staging array (R x C) into the padded device layout.
+template <typename T>
+__global__ void k_scatter_interior(T* __restrict__ dst, const T* __restrict__ src, Geom g) {
+    const long long n = (long long)g.R * g.C;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(k / g.C), j = (int)(k - (long long)i * g.C);
+        dst[dev_index(g, i + 1, j + 1)] = src[k];
+    }
+}
+
+template <typename T>
+__global__ void k_gather_interior(T* __restrict__ dst, const T* __restrict__ src, Geom g) {
+    const long long n = (long long)g.R * g.C;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(k / g.C), j = (int)(k - (long long)i * g.C);
+        dst[k] = src[dev_index(g, i + 1, j + 1)];
+    }
+}
+
+// Add-module initial condition, valid cells only (src/WDPMCL.c:778-792).
+template <typename T>
+__global__ void k_apply_add(T* __restrict__ w, const T* __restrict__ d, Geom g, T nodata, T depth, T depth_rof) {
+    const long long n = (long long)g.R * g.C;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(k / g.C), j = (int)(k - (long long)i * g.C);
+        const size_t a = dev_index(g, i + 1, j + 1);
+        if (d[a] > nodata) {
+            T v = w[a];
+            if (v > T(0)) v += depth;
+            if (v <= T(0)) v = depth_rof;
+            w[a] = v;
+        }
+    }
+}
+
+// Subtract-module initial condition (src/WDPMCL.c:919-926): max(w - depth, 0) with the
+// host macro's tie rule (a > b ? a : b).
+template <typename T>
+__global__ void k_apply_subtract(T* __restrict__ w, const T* __restrict__ d, Geom g, T nodata, T depth) {
+    const long long n = (long long)g.R * g.C;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(k / g.C), j = (int)(k - (long long)i * g.C);
+        const size_t a = dev_index(g, i + 1, j + 1);
+        if (d[a] > nodata) {
+            const T v = w[a] - depth;
+            w[a] = (v > T(0)) ? v : T(0);
+        }
+    }
+}
+
+// Block prologue (src/WDPMCL.c:1055-1073): w < thres -> 0 over the whole padded
+// grid (margins are 0 and stay 0), then snapshot.
+template <typename T>
+__global__ void k_block_prologue(T* __restrict__ w, T* __restrict__ oldw, long long n, T thres) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        T v = w[i];
+        if (v < thres) v = T(0);
+        w[i] = v;
+        oldw[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Convergence + water balance (src/WDPMCL.c:1239-1268), two stages, fixed order.
+// ---------------------------------------------------------------------------
+
+struct BlockPartial {
+    double max_diff;
+    double sum;
+    unsigned long long wet;
+};
+
+template <typename T, int NTHREADS>
+__global__ void __launch_bounds__(NTHREADS)
+k_block_reduce_stage1(const T* __restrict__ w, const T* __restrict__ oldw, const T* __restrict__ d,
+                      long long n, T nodata, BlockPartial* __restrict__ partials) {
+    T md = T(0);
+    double sum = 0.0;
+    unsigned long long wet = 0;
+    for (long long i = blockIdx.x * (long long)NTHREADS + threadIdx.x; i < n; i += (long long)gridDim.x * NTHREADS) {
+        if (d[i] > nodata) {
+            const T v = w[i];
+            T df = v - oldw[i];
+            df = df < T(0) ? -df : df;
+            md = df > md ? df : md;
+            sum += (double)v;
+            wet += (v > T(0)) ? 1ull : 0ull;
+        }
+    }
+    double mdd = (double)md;
+    for (int off = 16; off > 0; off >>= 1) {
+        const double om = __shfl_down_sync(0xffffffffu, mdd, off);
+        mdd = om > mdd ? om : mdd;
+        sum += __shfl_down_sync(0xffffffffu, sum, off);
+        wet += __shfl_down_sync(0xffffffffu, wet, off);
+    }
+    __shared__ double s_md[NTHREADS / 32];
+    __shared__ double s_sum[NTHREADS / 32];
+    __shared__ unsigned long long s_wet[NTHREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_md[warp] = mdd; s_sum[warp] = sum; s_wet[warp] = wet; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        BlockPartial p{0.0, 0.0, 0ull};
+        for (int k = 0; k < NTHREADS / 32; k++) {
+            p.max_diff = s_md[k] > p.max_diff ? s_md[k] : p.max_diff;
+            p.sum += s_sum[k];
+            p.wet += s_wet[k];
+        }
+        partials[blockIdx.x] = p;
+    }
+}
+
+__global__ void k_block_reduce_stage2(const BlockPartial* __restrict__ partials, int n, BlockPartial* __restrict__ out) {
+    // single thread, fixed order: the sum is reproducible run to run
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        BlockPartial p{0.0, 0.0, 0ull};
+        for (int k = 0; k < n; k++) {
+            p.max_diff = partials[k].max_diff > p.max_diff ? partials[k].max_diff : p.max_diff;
+            p.sum += partials[k].sum;
+            p.wet += partials[k].wet;
+        }
+        *out = p;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Drain outlet search (src/WDPMCL.c:1005-1017): min dem over dem > 0, first in
+// row-major order of the padded grid on ties.
+// ---------------------------------------------------------------------------
+
+struct OutletCand {
+    double elev;
+    long long index;  // i*(C+2)+j in padded coordinates; -1 = none
+};
+
+__device__ __forceinline__ OutletCand better(OutletCand a, OutletCand b) {
+    if (a.index < 0) return b;
+    if (b.index < 0) return a;
+    if (b.elev < a.elev || (b.elev == a.elev && b.index < a.index)) return b;
+    return a;
+}
+
+template <typename T, int NTHREADS>
+__global__ void __launch_bounds__(NTHREADS)
+k_find_outlet_stage1(const T* __restrict__ d, Geom g, OutletCand* __restrict__ partials) {
+    OutletCand best{1.0e8, -1};  // the reference starts from mindrain = 100000000 with strict '<'
+    const long long n = (long long)(g.R + 2) * (g.C + 2);
+    for (long long k = blockIdx.x * (long long)NTHREADS + threadIdx.x; k < n; k += (long long)gridDim.x * NTHREADS) {
+        const int i = (int)(k / (g.C + 2)), j = (int)(k - (long long)i * (g.C + 2));
+        const double v = (double)d[dev_index(g, i, j)];
+        if (v > 0.0 && v < 1.0e8) best = better(best, OutletCand{v, k});
+    }
+    __shared__ OutletCand s[NTHREADS];
+    s[threadIdx.x] = best;
+    __syncthreads();
+    for (int off = NTHREADS / 2; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) s[threadIdx.x] = better(s[threadIdx.x], s[threadIdx.x + off]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = s[0];
+}
+
+__global__ void k_find_outlet_stage2(const OutletCand* __restrict__ partials, int n, OutletCand* __restrict__ out) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        OutletCand best{1.0e8, -1};
+        for (int k = 0; k < n; k++) best = better(best, partials[k]);
+        *out = best;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Drain bookkeeping. totaldrain is one accumulator in the solver's precision
+// (src/runoff.cl:108). An event is the pair of addends of one outlet contact,
+// folded as (totaldrain + w_outlet) + w_centre, in sub-pass order.
+// ---------------------------------------------------------------------------
+
+template <typename T>
+struct DrainEvent {
+    T w_outlet;
+    T w_centre;
+    int valid;
+    int pad;
+};
+
+template <typename T>
+struct DrainState {
+    T* totaldrain;          // device scalar
+    DrainEvent<T>* events;  // [2][9*kMaxItersPerLaunch], double-buffered by launch parity
+    int drainrow, draincol; // padded coordinates; (-10,-10) when unset
+};
+
+constexpr int kEventsPerBuffer = 9 * kMaxItersPerLaunch;
+
+template <typename T>
+__device__ __forceinline__ void fold_events(DrainState<T> ds, int parity) {
+    DrainEvent<T>* ev = ds.events + parity * kEventsPerBuffer;
+    T td = *ds.totaldrain;
+    for (int e = 0; e < kEventsPerBuffer; e++) {
+        if (ev[e].valid) {
+            td = td + ev[e].w_outlet;
+            td = td + ev[e].w_centre;
+            ev[e].valid = 0;
+        }
+    }
+    *ds.totaldrain = td;
+}
+
+template <typename T>
+__global__ void k_fold_events(DrainState<T> ds, int parity) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) fold_events(ds, parity);
+}
+
+// ---------------------------------------------------------------------------
+// Colour kernel: one launch per colour sub-pass on global memory, in place.
+// This is the reference's schedule (src/WDPMCL.c:1184-1206) - the baseline the
+// fused kernel is checked against and the path for grids too small to tile.
+// Thread (gx, gy) owns centre row = oi + 3*gy, col = oj + 3*gx (1-based padded).
+// ---------------------------------------------------------------------------
+
+template <typename T, int MODULE>
+__global__ void __launch_bounds__(256)
+k_colour(T* __restrict__ w, const T* __restrict__ d, Geom g, T nodata, int oi, int oj, DrainState<T> ds) {
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gy = blockIdx.y * blockDim.y + threadIdx.y;
+    const int row = oi + 3 * gy, col = oj + 3 * gx;
+    if (row > g.R || col > g.C) return;
+    const size_t c = dev_index(g, row, col);
+    T* w1 = w + c;
+    const T* d1 = d + c;
+    if (MODULE == kDrain) {
+        const int orow = ds.drainrow - row, ocol = ds.draincol - col;
+        if (orow >= -1 && orow <= 1 && ocol >= -1 && ocol <= 1) {
+            if (orow == 0 && ocol == 0) return;  // the outlet is never a centre (src/runoff.cl:179)
+            T evo, evc;
+            bool drained;
+            relax_tile_at_outlet<T>(w1 - g.pitch, w1, w1 + g.pitch, d1 - g.pitch, d1, d1 + g.pitch, 0, nodata,
+                                    orow, ocol, &evo, &evc, &drained);
+            if (drained) {  // single writer per sub-pass
+                T td = *ds.totaldrain;
+                td = td + evo;
+                td = td + evc;
+                *ds.totaldrain = td;
+            }
+            return;
+        }
+    }
+    relax_tile<T, MODULE>(w1 - g.pitch, w1, w1 + g.pitch, d1 - g.pitch, d1, d1 + g.pitch, 0, nodata);
+}
+
+// ---------------------------------------------------------------------------
+// Fused kernel: K whole iterations (9K colour sub-passes) per launch.
+// See mw_schedule.h for the schedule. Data movement is TMA bulk copies
+// (cp.async.bulk, SASS UBLKCP) global -> shared completing on mbarriers, and
+// shared -> global bulk stores in bulk async-groups; compute is plain SIMT on
+// the shared-memory row ring (stride-3 access is bank-conflict free).
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+template <typename T>
+struct FusedParams {
+    const T* w_in;
+    T* w_out;
+    const T* dem;
+    Geom g;
+    T nodata;
+    int n_strips;
+    int chunk_triples;  // owned row triples per CTA
+    int total_triples;  // ceil((R+2)/3)
+    int launch_parity;  // drain event buffer written by this launch
+    DrainState<T> ds;
+};
+
+template <typename CFG, typename T>
+constexpr size_t fused_smem_bytes() {
+    return (size_t)2 * CFG::NRING * CFG::W * sizeof(T) + CFG::NSTAGE * sizeof(uint64_t) + 16;
+}
+
+template <typename T, int MODULE, typename CFG, int NTHREADS, int MINB>
+__global__ void __launch_bounds__(NTHREADS, MINB)
+k_fused(const FusedParams<T> p) {
+    constexpr int W = CFG::W, NT = CFG::NT, NPH = CFG::NPH, NRING = CFG::NRING, NSTAGE = CFG::NSTAGE, PF = CFG::PF;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* ring_w = reinterpret_cast<T*>(smem_raw);
+    T* ring_d = ring_w + (size_t)NRING * W;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring_d + (size_t)NRING * W);
+
+    const int tid = threadIdx.x;
+    const int strip = blockIdx.x % p.n_strips;
+    const int chunk = blockIdx.x / p.n_strips;
+    MwTile<CFG> tile;
+    tile.init(strip, chunk, p.chunk_triples, p.total_triples);
+
+    if (MODULE == kDrain && blockIdx.x == 0 && tid == 0) fold_events(p.ds, p.launch_parity ^ 1);
+
+    if (tid == 0) {
+        for (int i = 0; i < NSTAGE; i++) mbar_init(&bars[i], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    constexpr uint32_t kRowBytes = W * sizeof(T);
+    // device column of window column 0; multiple of 4 elements by construction
+    const size_t col0 = (size_t)(tile.x0 + kPadLeft);
+
+    auto issue_loads = [&](int s) {  // thread 0 only: stage the A-type rows of step s
+        uint64_t* bar = &bars[s % NSTAGE];
+        int nrows = 0;
+        for (int t = 0; t < NT; t++)
+            if (tile.staged(tile.triple(s, 0, t))) nrows += 3;
+        if (nrows == 0) return;
+        mbar_expect_tx(bar, (uint32_t)(2 * nrows) * kRowBytes);
+        for (int t = 0; t < NT; t++) {
+            const int m = tile.triple(s, 0, t);
+            if (!tile.staged(m)) continue;
+            for (int k = 0; k < 3; k++) {
+                const int row = 3 * m + k;
+                const size_t src = (size_t)(row + kPadTop) * (size_t)p.g.pitch + col0;
+                const int slot = tile.ring_slot(row);
+                bulk_load(ring_w + (size_t)slot * W, p.w_in + src, kRowBytes, bar);
+                bulk_load(ring_d + (size_t)slot * W, p.dem + src, kRowBytes, bar);
+            }
+        }
+    };
+    auto step_has_loads = [&](int s) {
+        for (int t = 0; t < NT; t++)
+            if (tile.staged(tile.triple(s, 0, t))) return true;
+        return false;
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < PF && s < tile.n_steps; s++) issue_loads(s);
+    }
+
+    for (int s = 0; s < tile.n_steps; s++) {
+        // issue the prefetch for step s+PF: its ring slots were released at the end of step s-1
+        if (tid == 0 && s + PF < tile.n_steps) issue_loads(s + PF);
+        if (step_has_loads(s)) mbar_wait(&bars[s % NSTAGE], (uint32_t)((s / NSTAGE) & 1));
+
+#pragma unroll 1
+        for (int cofs = 0; cofs < 3; cofs++) {
+            constexpr int nc = CFG::NC;
+            constexpr int nitems = NPH * NT * nc;
+            for (int item = tid; item < nitems; item += NTHREADS) {
+                const int c = item % nc;
+                const int pt = item / nc;
+                const int t = pt % NT;
+                const int ph = pt / NT;
+                const int q = ph % 3;
+                const int m = tile.triple(s, ph, t);
+                if (!tile.runnable(m, q)) continue;
+                const int row0 = 3 * m + q;
+                int s0 = tile.ring_slot(row0);
+                int s1 = s0 + 1; if (s1 == NRING) s1 = 0;
+                int s2 = s1 + 1; if (s2 == NRING) s2 = 0;
+                const int j = 3 * c + cofs + 1;  // centre column inside the window
+                T* w0 = ring_w + s0 * W; T* w1 = ring_w + s1 * W; T* w2 = ring_w + s2 * W;
+                const T* d0 = ring_d + s0 * W; const T* d1 = ring_d + s1 * W; const T* d2 = ring_d + s2 * W;
+                if (MODULE == kDrain) {
+                    const int crow = row0 + 1, ccol = tile.x0 + j;
+                    const int orow = p.ds.drainrow - crow, ocol = p.ds.draincol - ccol;
+                    if (orow >= -1 && orow <= 1 && ocol >= -1 && ocol <= 1) {
+                        if (orow == 0 && ocol == 0) continue;
+                        T evo, evc;
+                        bool drained;
+                        relax_tile_at_outlet<T>(w0, w1, w2, d0, d1, d2, j, p.nodata, orow, ocol, &evo, &evc, &drained);
+                        // only the CTA that owns the centre reports the event (halo copies recompute it)
+                        if (drained && tile.owns_row(crow) && tile.owns_col(ccol)) {
+                            DrainEvent<T>* ev = p.ds.events + p.launch_parity * kEventsPerBuffer + (ph / 3) * 9 + q * 3 + cofs;
+                            ev->w_outlet = evo;
+                            ev->w_centre = evc;
+                            ev->valid = 1;
+                        }
+                        continue;
+                    }
+                }
+                relax_tile<T, MODULE>(w0, w1, w2, d0, d1, d2, j, p.nodata);
+            }
+            if (cofs == 2) fence_proxy_async();  // make this step's smem writes visible to the bulk-store engine
+            __syncthreads();
+        }
+
+        if (tid == 0) {
+            // rows finished by the last phase in this step: C-type rows 3m+2 .. 3m+4
+            bool any = false;
+            for (int t = 0; t < NT; t++) {
+                const int m = tile.triple(s, NPH - 1, t);
+                for (int k = 0; k < 3; k++) {
+                    const int row = 3 * m + 2 + k;
+                    if (!tile.owns_row(row)) continue;
+                    const size_t dst = (size_t)(row + kPadTop) * (size_t)p.g.pitch + col0 + CFG::HL;
+                    bulk_store(p.w_out + dst, ring_w + (size_t)tile.ring_slot(row) * W + CFG::HL, CFG::TWV * sizeof(T));
+                    any = true;
+                }
+            }
+            if (any) bulk_commit();
+            // ring slots reused by the next prefetch must have been read out by their stores:
+            // allow only the group committed just now to be in flight
+            bulk_wait_read<1>();
+        }
+        // No extra barrier: the next loads are issued by thread 0 after its wait above, and every
+        // thread's next access to a reloaded slot is behind that load's mbarrier.
+    }
+    if (tid == 0) bulk_wait_read<0>();
+}
+
+}  // namespace wdpm

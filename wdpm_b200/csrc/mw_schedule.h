@@ -48,20 +48,25 @@ struct MwCfg {
     static constexpr int LAG = NT + 1;    // triple lag between consecutive phases
     static constexpr int HL = 12 * K;     // left halo columns  (needs >= 9K-1; multiple of 12 keeps 16 B alignment and mod-3 phase)
     static constexpr int HR_NEED = 18 * K - 2;  // right halo columns needed
-    // the last (W mod 3) window columns never hold a complete tile for oj=1: budget 2 spare
-    static constexpr int TWV = ((W - 2 - HL - HR_NEED) / 12) * 12;  // owned columns per strip
+    // tiles per row triple, the same for every tile-start column offset cofs = oj-1 in {0,1,2}:
+    // tile c starts at window column 3c+cofs and must end inside the window for cofs = 2.
+    static constexpr int NC = (W - 5) / 3 + 1;
+    // the oj=1 tessellation covers window columns [0, 3*NC): that is the width the halos eat into
+    static constexpr int TWV = ((3 * NC - HL - HR_NEED) / 12) * 12;  // owned columns per strip
     static constexpr int TOP_TRIPLES = K;      // triples staged above the owned rows
     static constexpr int BOT_TRIPLES = 2 * K;  // triples staged below
-    static constexpr int NRING_MIN = 3 * NT * (PF + 1) + 3 * (NPH - 1) * LAG - 2;
-    static constexpr int NRING = ((NRING_MIN + 2) / 3) * 3;  // ring rows (multiple of 3)
+    // Ring rows: from the oldest row whose write-back may still be reading shared memory (the
+    // store group of the previous step is allowed to be in flight) to the newest prefetched row.
+    static constexpr int NRING_MIN = 3 * NT * (PF + 2) + 3 * (NPH - 1) * LAG - 2;
+#ifndef WDPM_NRING_DELTA
+#define WDPM_NRING_DELTA 0 /* tests shrink the ring to prove the hazard checks fire */
+#endif
+    static constexpr int NRING = ((NRING_MIN + 2) / 3) * 3 + WDPM_NRING_DELTA;  // ring rows (multiple of 3)
     static constexpr int NSTAGE = PF + 1;      // load barriers
     static_assert(W % 4 == 0, "window rows must be 16-byte multiples");
     static_assert(TWV > 0, "window too narrow for its halos");
     static_assert(K >= 1 && K <= kMaxItersPerLaunch, "iterations per launch");
     static_assert(HL <= kPadLeft, "left halo exceeds the device margin");
-
-    // number of tiles per row triple for tile-start column offset cofs (= oj-1)
-    WDPM_SCHED_HD static constexpr int tiles_per_row(int cofs) { return (W - 3 - cofs) / 3 + 1; }
 };
 
 // Per-CTA view of the schedule. All rows/cols are PADDED grid coordinates

@@ -1,0 +1,696 @@
+// C ABI of the B200-native WDPM redistribution solver: device state, launch
+// plumbing and the per-block driver. Declarations and the mapping to the
+// reference's call sites are in include/wdpm_b200.h.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/wdpm_b200.h"
+#include "kernels.cuh"
+
+using namespace wdpm;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(e_ == cudaErrorMemoryAllocation ? WDPM_E_NOMEM : WDPM_E_CUDA,               \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_));                        \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// Fused-kernel variants. One entry = one instantiation of k_fused per module.
+// ---------------------------------------------------------------------------
+
+template <typename T>
+using FusedLaunchFn = cudaError_t (*)(const FusedParams<T>&, int grid, cudaStream_t);
+
+template <typename T>
+struct FusedVariant {
+    int W, TWV, HL, K, NT, PF, nthreads, minb;
+    size_t smem;
+    FusedLaunchFn<T> launch[3];
+    cudaError_t (*prepare)();
+};
+
+template <typename T, int MODULE, typename CFG, int NTHREADS, int MINB>
+cudaError_t launch_fused(const FusedParams<T>& p, int grid, cudaStream_t st) {
+    k_fused<T, MODULE, CFG, NTHREADS, MINB><<<grid, NTHREADS, fused_smem_bytes<CFG, T>(), st>>>(p);
+    return cudaGetLastError();
+}
+
+template <typename T, typename CFG, int NTHREADS, int MINB>
+cudaError_t prepare_fused() {
+    const int smem = (int)fused_smem_bytes<CFG, T>();
+    cudaError_t e;
+    e = cudaFuncSetAttribute(k_fused<T, kAdd, CFG, NTHREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_fused<T, kSubtract, CFG, NTHREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_fused<T, kDrain, CFG, NTHREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
+template <typename T, typename CFG, int NTHREADS, int MINB>
+FusedVariant<T> make_variant() {
+    FusedVariant<T> v;
+    v.W = CFG::W; v.TWV = CFG::TWV; v.HL = CFG::HL; v.K = CFG::K; v.NT = CFG::NT; v.PF = CFG::PF;
+    v.nthreads = NTHREADS; v.minb = MINB;
+    v.smem = fused_smem_bytes<CFG, T>();
+    v.launch[kAdd] = launch_fused<T, kAdd, CFG, NTHREADS, MINB>;
+    v.launch[kSubtract] = launch_fused<T, kSubtract, CFG, NTHREADS, MINB>;
+    v.launch[kDrain] = launch_fused<T, kDrain, CFG, NTHREADS, MINB>;
+    v.prepare = prepare_fused<T, CFG, NTHREADS, MINB>;
+    return v;
+}
+
+// Variant ids are 1-based in the ABI. 1 is the production tiling for each
+// precision; the small windows exist so tests can force many strips / chunks /
+// iterations-per-launch on small grids.
+template <typename T>
+const std::vector<FusedVariant<T>>& fused_variants();
+
+template <>
+const std::vector<FusedVariant<double>>& fused_variants<double>() {
+    static const std::vector<FusedVariant<double>> v = {
+        make_variant<double, MwCfg<512, 1, 1, 2>, 512, 1>(),  // 1: 192 KB ring, one CTA per SM
+        make_variant<double, MwCfg<64, 1, 1, 1>, 128, 1>(),   // 2: test
+        make_variant<double, MwCfg<128, 1, 2, 2>, 256, 1>(),  // 3: test, two iterations per launch
+        make_variant<double, MwCfg<320, 2, 1, 2>, 512, 1>(),  // 4: two triples per phase
+        make_variant<double, MwCfg<256, 1, 1, 2>, 256, 2>(),  // 5: two CTAs per SM
+        make_variant<double, MwCfg<256, 1, 2, 2>, 512, 1>(),  // 6: two iterations per launch
+    };
+    return v;
+}
+template <>
+const std::vector<FusedVariant<float>>& fused_variants<float>() {
+    static const std::vector<FusedVariant<float>> v = {
+        make_variant<float, MwCfg<512, 1, 1, 2>, 256, 2>(),   // 1: 96 KB ring, two CTAs per SM
+        make_variant<float, MwCfg<64, 1, 1, 1>, 128, 1>(),    // 2: test
+        make_variant<float, MwCfg<128, 1, 2, 2>, 256, 1>(),   // 3: test, two iterations per launch
+        make_variant<float, MwCfg<384, 2, 1, 2>, 512, 1>(),   // 4
+        make_variant<float, MwCfg<1024, 1, 1, 2>, 512, 1>(),  // 5: wide window
+        make_variant<float, MwCfg<512, 1, 2, 2>, 512, 1>(),   // 6: two iterations per launch
+    };
+    return v;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+
+struct wdpm_solver {
+    wdpm_config cfg{};
+    int dtype = WDPM_F64, module = WDPM_ADD;
+    size_t esize = 8;
+    Geom g{};
+    int kernel = WDPM_KERNEL_COLOUR;
+    int variant = 0;  // 0-based index into fused_variants
+    int n_strips = 0, total_triples = 0, chunk_triples = 0, n_chunks = 0;
+    int sm_count = 0;
+    int device = 0;
+
+    void* dem = nullptr;
+    void* w[2] = {nullptr, nullptr};
+    void* oldw = nullptr;
+    int cur = 0;
+    bool have_dem = false;
+
+    void* totaldrain = nullptr;  // device scalar (T)
+    void* events = nullptr;      // DrainEvent<T>[2][kEventsPerBuffer]
+    int drainrow = -10, draincol = -10;
+    int launch_parity = 0;
+
+    BlockPartial* partials = nullptr;
+    BlockPartial* d_result = nullptr;
+    BlockPartial* h_result = nullptr;  // pinned
+    OutletCand* outlet_partials = nullptr;
+    OutletCand* d_outlet = nullptr;
+    int reduce_blocks = 0;
+
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    long long launches = 0;
+    long long device_bytes = 0;
+};
+
+namespace {
+
+template <typename T>
+DrainState<T> drain_state(wdpm_solver* s) {
+    DrainState<T> ds;
+    ds.totaldrain = static_cast<T*>(s->totaldrain);
+    ds.events = static_cast<DrainEvent<T>*>(s->events);
+    ds.drainrow = s->drainrow;
+    ds.draincol = s->draincol;
+    return ds;
+}
+
+int grid_for(long long n, int threads, int sm_count) {
+    long long b = (n + threads - 1) / threads;
+    const long long cap = (long long)sm_count * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+template <typename T>
+int colour_subpass(wdpm_solver* s, int oi, int oj) {
+    const dim3 block(32, 8);
+    const int ncx = (s->g.C - oj) / 3 + 1, ncy = (s->g.R - oi) / 3 + 1;
+    if (ncx <= 0 || ncy <= 0) return WDPM_OK;
+    const dim3 grid((ncx + block.x - 1) / block.x, (ncy + block.y - 1) / block.y);
+    T* w = static_cast<T*>(s->w[s->cur]);
+    const T* d = static_cast<const T*>(s->dem);
+    const T nodata = (T)s->cfg.nodata;
+    DrainState<T> ds = drain_state<T>(s);
+    switch (s->module) {
+        case WDPM_ADD: k_colour<T, kAdd><<<grid, block, 0, s->stream>>>(w, d, s->g, nodata, oi, oj, ds); break;
+        case WDPM_SUBTRACT: k_colour<T, kSubtract><<<grid, block, 0, s->stream>>>(w, d, s->g, nodata, oi, oj, ds); break;
+        default: k_colour<T, kDrain><<<grid, block, 0, s->stream>>>(w, d, s->g, nodata, oi, oj, ds); break;
+    }
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return WDPM_OK;
+}
+
+template <typename T>
+int colour_iterations(wdpm_solver* s, int n) {
+    for (int it = 0; it < n; it++)
+        for (int oi = 1; oi <= 3; oi++)
+            for (int oj = 1; oj <= 3; oj++) {
+                const int rc = colour_subpass<T>(s, oi, oj);
+                if (rc) return rc;
+            }
+    return WDPM_OK;
+}
+
+template <typename T>
+int fused_iterations(wdpm_solver* s, int n) {
+    const FusedVariant<T>& v = fused_variants<T>()[s->variant];
+    const int n_launch = n / v.K;
+    for (int l = 0; l < n_launch; l++) {
+        FusedParams<T> p;
+        p.w_in = static_cast<const T*>(s->w[s->cur]);
+        p.w_out = static_cast<T*>(s->w[s->cur ^ 1]);
+        p.dem = static_cast<const T*>(s->dem);
+        p.g = s->g;
+        p.nodata = (T)s->cfg.nodata;
+        p.n_strips = s->n_strips;
+        p.chunk_triples = s->chunk_triples;
+        p.total_triples = s->total_triples;
+        p.launch_parity = s->launch_parity;
+        p.ds = drain_state<T>(s);
+        CUDA_TRY(v.launch[s->module](p, s->n_strips * s->n_chunks, s->stream));
+        s->launches++;
+        s->cur ^= 1;
+        s->launch_parity ^= 1;
+    }
+    if (s->module == WDPM_DRAIN && n_launch > 0) {
+        k_fold_events<T><<<1, 32, 0, s->stream>>>(drain_state<T>(s), s->launch_parity ^ 1);
+        s->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    // iterations that do not fill a launch run through the colour kernel (same results)
+    return colour_iterations<T>(s, n - n_launch * v.K);
+}
+
+template <typename T>
+int iterate_t(wdpm_solver* s, int n) {
+    if (s->kernel == WDPM_KERNEL_FUSED) return fused_iterations<T>(s, n);
+    return colour_iterations<T>(s, n);
+}
+
+int iterate(wdpm_solver* s, int n) {
+    return s->dtype == WDPM_F64 ? iterate_t<double>(s, n) : iterate_t<float>(s, n);
+}
+
+template <typename T>
+int run_block_t(wdpm_solver* s, int n_iters, wdpm_block_result* out) {
+    const long long n = s->g.cells_dev();
+    const long long launches0 = s->launches;
+    CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
+    k_block_prologue<T><<<grid_for(n, 256, s->sm_count), 256, 0, s->stream>>>(
+        static_cast<T*>(s->w[s->cur]), static_cast<T*>(s->oldw), n, (T)s->cfg.zero_threshold);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(s->ev[1], s->stream));
+    int rc = iterate_t<T>(s, n_iters);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
+    k_block_reduce_stage1<T, 256><<<s->reduce_blocks, 256, 0, s->stream>>>(
+        static_cast<const T*>(s->w[s->cur]), static_cast<const T*>(s->oldw), static_cast<const T*>(s->dem), n,
+        (T)s->cfg.nodata, s->partials);
+    k_block_reduce_stage2<<<1, 32, 0, s->stream>>>(s->partials, s->reduce_blocks, s->d_result);
+    s->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(s->h_result, s->d_result, sizeof(BlockPartial), cudaMemcpyDeviceToHost, s->stream));
+    T td = T(0);
+    CUDA_TRY(cudaMemcpyAsync(&td, s->totaldrain, sizeof(T), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (out) {
+        out->max_diff = s->h_result->max_diff;
+        out->masked_sum = s->h_result->sum;
+        out->wet_cells = (int64_t)s->h_result->wet;
+        out->total_drain = (double)td;
+        out->iterations = n_iters;
+        out->launches = (int32_t)(s->launches - launches0);
+        CUDA_TRY(cudaEventElapsedTime(&out->block_ms, s->ev[0], s->ev[3]));
+        CUDA_TRY(cudaEventElapsedTime(&out->iterate_ms, s->ev[1], s->ev[2]));
+    }
+    return WDPM_OK;
+}
+
+template <typename T>
+int fill_dem(wdpm_solver* s) {
+    const long long n = s->g.cells_dev();
+    k_fill<T><<<grid_for(n, 256, s->sm_count), 256, 0, s->stream>>>(static_cast<T*>(s->dem), n, (T)s->cfg.nodata);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return WDPM_OK;
+}
+
+void* interior_ptr(wdpm_solver* s, void* base) {
+    return static_cast<char*>(base) + ((size_t)(1 + kPadTop) * s->g.pitch + (size_t)(1 + kPadLeft)) * s->esize;
+}
+
+int upload_grid(wdpm_solver* s, void* dst_base, const void* host) {
+    CUDA_TRY(cudaMemcpy2DAsync(interior_ptr(s, dst_base), (size_t)s->g.pitch * s->esize, host, (size_t)s->g.C * s->esize,
+                               (size_t)s->g.C * s->esize, (size_t)s->g.R, cudaMemcpyHostToDevice, s->stream));
+    return WDPM_OK;
+}
+
+// Pick the number of row chunks: whole waves of CTAs, counting the per-chunk
+// pipeline fill (halo triples + phase lags) as wasted steps.
+void choose_chunks(wdpm_solver* s, int K, int NT, int minb, int forced_rows) {
+    const int total = s->total_triples;
+    if (forced_rows > 0) {
+        s->chunk_triples = (forced_rows + 2) / 3;
+        if (s->chunk_triples > total) s->chunk_triples = total;
+        s->n_chunks = (total + s->chunk_triples - 1) / s->chunk_triples;
+        return;
+    }
+    const int slots = s->sm_count * (minb > 0 ? minb : 1);
+    const int fill = 3 * K + (3 * K - 1) * (NT + 1);
+    double best_cost = 1e300;
+    int best_ct = total;
+    const int max_chunks = total / 16 > 0 ? total / 16 : 1;
+    for (int nch = 1; nch <= max_chunks && nch <= 4096; nch++) {
+        const int ct = (total + nch - 1) / nch;
+        const int real_nch = (total + ct - 1) / ct;
+        const long long ctas = (long long)real_nch * s->n_strips;
+        const long long waves = (ctas + slots - 1) / slots;
+        const double cost = (double)waves * (ct + fill);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best_ct = ct; }
+    }
+    s->chunk_triples = best_ct;
+    s->n_chunks = (total + best_ct - 1) / best_ct;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// extern "C"
+// ---------------------------------------------------------------------------
+
+extern "C" {
+
+const char* wdpm_last_error(void) { return g_err.c_str(); }
+int wdpm_abi_version(void) { return WDPM_ABI_VERSION; }
+
+int wdpm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int wdpm_fused_variant_info(int32_t variant, int32_t dtype, int32_t* window_cols, int32_t* strip_cols,
+                            int32_t* iters_per_launch, int32_t* cta_threads, int32_t* smem_bytes) {
+    if (variant < 1) return fail(WDPM_E_ARG, "variant ids start at 1");
+    int W, TWV, K, nt; size_t smem;
+    if (dtype == WDPM_F64) {
+        const auto& v = fused_variants<double>();
+        if (variant > (int)v.size()) return fail(WDPM_E_ARG, "no such fused variant");
+        W = v[variant - 1].W; TWV = v[variant - 1].TWV; K = v[variant - 1].K; nt = v[variant - 1].nthreads; smem = v[variant - 1].smem;
+    } else if (dtype == WDPM_F32) {
+        const auto& v = fused_variants<float>();
+        if (variant > (int)v.size()) return fail(WDPM_E_ARG, "no such fused variant");
+        W = v[variant - 1].W; TWV = v[variant - 1].TWV; K = v[variant - 1].K; nt = v[variant - 1].nthreads; smem = v[variant - 1].smem;
+    } else {
+        return fail(WDPM_E_ARG, "dtype must be WDPM_F32 or WDPM_F64");
+    }
+    if (window_cols) *window_cols = W;
+    if (strip_cols) *strip_cols = TWV;
+    if (iters_per_launch) *iters_per_launch = K;
+    if (cta_threads) *cta_threads = nt;
+    if (smem_bytes) *smem_bytes = (int32_t)smem;
+    return WDPM_OK;
+}
+
+int wdpm_create(const wdpm_config* cfg, wdpm_solver** out) {
+    if (!cfg || !out) return fail(WDPM_E_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(wdpm_config)) return fail(WDPM_E_ARG, "wdpm_config.struct_size mismatch (ABI version?)");
+    if (cfg->rows < 1 || cfg->cols < 1) return fail(WDPM_E_ARG, "rows and cols must be positive");
+    if (cfg->dtype != WDPM_F32 && cfg->dtype != WDPM_F64) return fail(WDPM_E_ARG, "dtype must be WDPM_F32 or WDPM_F64");
+    if (cfg->module < WDPM_ADD || cfg->module > WDPM_DRAIN) return fail(WDPM_E_ARG, "unknown module");
+    if (cfg->kernel < WDPM_KERNEL_AUTO || cfg->kernel > WDPM_KERNEL_FUSED) return fail(WDPM_E_ARG, "unknown kernel selector");
+    if (cfg->stripe_row0 != 0 || (cfg->stripe_rows != 0 && cfg->stripe_rows != cfg->rows))
+        return fail(WDPM_E_UNSUPPORTED, "row-stripe solvers are not implemented in this build");
+    if ((long long)(cfg->rows + 64) * (long long)(cfg->cols + 2048) > (1ll << 40)) return fail(WDPM_E_ARG, "grid too large");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(WDPM_E_CUDA, "no CUDA device: this library has no CPU path");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(WDPM_E_ARG, "device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(cfg->device));
+
+    wdpm_solver* s = new (std::nothrow) wdpm_solver();
+    if (!s) return fail(WDPM_E_NOMEM, "host allocation failed");
+    s->cfg = *cfg;
+    s->dtype = cfg->dtype;
+    s->module = cfg->module;
+    s->esize = cfg->dtype == WDPM_F64 ? 8 : 4;
+    s->device = cfg->device;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, cfg->device);
+    if (e != cudaSuccess) { delete s; return fail(WDPM_E_CUDA, cudaGetErrorString(e)); }
+    s->sm_count = prop.multiProcessorCount;
+
+    // kernel + variant
+    const long long cells = (long long)(cfg->rows + 2) * (cfg->cols + 2);
+    s->kernel = cfg->kernel == WDPM_KERNEL_AUTO ? (cells >= (1ll << 20) ? WDPM_KERNEL_FUSED : WDPM_KERNEL_COLOUR) : cfg->kernel;
+    const int nvar = s->dtype == WDPM_F64 ? (int)fused_variants<double>().size() : (int)fused_variants<float>().size();
+    int variant = cfg->fused_variant;
+    if (variant < 0 || variant > nvar) { delete s; return fail(WDPM_E_ARG, "fused_variant out of range"); }
+    if (variant == 0) {
+        variant = 1;
+        if (cfg->iters_per_launch > 1) {
+            variant = 0;
+            for (int i = 0; i < nvar; i++) {
+                const int K = s->dtype == WDPM_F64 ? fused_variants<double>()[i].K : fused_variants<float>()[i].K;
+                const int W = s->dtype == WDPM_F64 ? fused_variants<double>()[i].W : fused_variants<float>()[i].W;
+                if (K == cfg->iters_per_launch && W >= 256) { variant = i + 1; break; }
+            }
+            if (variant == 0) { delete s; return fail(WDPM_E_UNSUPPORTED, "no production fused variant with that iters_per_launch"); }
+        }
+    }
+    s->variant = variant - 1;
+    int W, TWV, HL, K, NT, minb;
+    cudaError_t (*prepare)();
+    if (s->dtype == WDPM_F64) {
+        const auto& v = fused_variants<double>()[s->variant];
+        W = v.W; TWV = v.TWV; HL = v.HL; K = v.K; NT = v.NT; minb = v.minb; prepare = v.prepare;
+    } else {
+        const auto& v = fused_variants<float>()[s->variant];
+        W = v.W; TWV = v.TWV; HL = v.HL; K = v.K; NT = v.NT; minb = v.minb; prepare = v.prepare;
+    }
+    if (s->kernel == WDPM_KERNEL_FUSED) {
+        e = prepare();
+        if (e != cudaSuccess) { delete s; return fail(WDPM_E_CUDA, std::string("fused kernel setup: ") + cudaGetErrorString(e)); }
+    }
+
+    // geometry (the tests' schedule emulator uses the same formulas)
+    s->g.R = cfg->rows;
+    s->g.C = cfg->cols;
+    s->n_strips = (cfg->cols + 2 + TWV - 1) / TWV;
+    s->total_triples = (cfg->rows + 2 + 2) / 3;
+    s->g.pitch = ((kPadLeft + s->n_strips * TWV + (W - TWV - HL) + 31) / 32) * 32;
+    s->g.nrows_dev = kPadTop + 3 * (s->total_triples + 2 * kMaxItersPerLaunch) + 3;
+    choose_chunks(s, K, NT, minb, cfg->fused_chunk_rows);
+
+    auto cleanup = [&](int code, const std::string& msg) {
+        wdpm_destroy(s);
+        return fail(code, msg);
+    };
+    const size_t grid_bytes = (size_t)s->g.cells_dev() * s->esize;
+    void** grids[4] = {&s->dem, &s->w[0], &s->w[1], &s->oldw};
+    for (auto gp : grids) {
+        e = cudaMalloc(gp, grid_bytes);
+        if (e != cudaSuccess) return cleanup(WDPM_E_NOMEM, std::string("cudaMalloc grid: ") + cudaGetErrorString(e));
+        s->device_bytes += (long long)grid_bytes;
+    }
+    s->reduce_blocks = s->sm_count * 8;
+    const size_t ev_bytes = 2 * kEventsPerBuffer * (s->dtype == WDPM_F64 ? sizeof(DrainEvent<double>) : sizeof(DrainEvent<float>));
+    if ((e = cudaMalloc(&s->totaldrain, 8)) != cudaSuccess || (e = cudaMalloc(&s->events, ev_bytes)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&s->partials, sizeof(BlockPartial) * s->reduce_blocks)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&s->d_result, sizeof(BlockPartial))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&s->outlet_partials, sizeof(OutletCand) * s->reduce_blocks)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&s->d_outlet, sizeof(OutletCand))) != cudaSuccess ||
+        (e = cudaHostAlloc((void**)&s->h_result, sizeof(BlockPartial), cudaHostAllocDefault)) != cudaSuccess)
+        return cleanup(WDPM_E_NOMEM, std::string("cudaMalloc scratch: ") + cudaGetErrorString(e));
+    if ((e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return cleanup(WDPM_E_CUDA, cudaGetErrorString(e));
+    s->stream = s->own_stream;
+    for (auto& evn : s->ev)
+        if ((e = cudaEventCreate(&evn)) != cudaSuccess) return cleanup(WDPM_E_CUDA, cudaGetErrorString(e));
+
+    if ((e = cudaMemsetAsync(s->w[0], 0, grid_bytes, s->stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(s->w[1], 0, grid_bytes, s->stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(s->oldw, 0, grid_bytes, s->stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(s->totaldrain, 0, 8, s->stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(s->events, 0, ev_bytes, s->stream)) != cudaSuccess)
+        return cleanup(WDPM_E_CUDA, cudaGetErrorString(e));
+    int rc = s->dtype == WDPM_F64 ? fill_dem<double>(s) : fill_dem<float>(s);
+    if (rc) { wdpm_destroy(s); return rc; }
+    if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess) return cleanup(WDPM_E_CUDA, cudaGetErrorString(e));
+    *out = s;
+    return WDPM_OK;
+}
+
+int wdpm_destroy(wdpm_solver* s) {
+    if (!s) return WDPM_OK;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    void* ptrs[] = {s->dem, s->w[0], s->w[1], s->oldw, s->totaldrain, s->events, s->partials, s->d_result, s->outlet_partials, s->d_outlet};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (s->h_result) cudaFreeHost(s->h_result);
+    for (auto& evn : s->ev)
+        if (evn) cudaEventDestroy(evn);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    cudaGetLastError();
+    delete s;
+    return WDPM_OK;
+}
+
+int wdpm_set_stream(wdpm_solver* s, void* cuda_stream) {
+    if (!s) return fail(WDPM_E_ARG, "null solver");
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s->own_stream;
+    return WDPM_OK;
+}
+
+int wdpm_synchronize(wdpm_solver* s) {
+    if (!s) return fail(WDPM_E_ARG, "null solver");
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return WDPM_OK;
+}
+
+int wdpm_upload(wdpm_solver* s, const void* dem, const void* water) {
+    if (!s || !dem) return fail(WDPM_E_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    int rc = upload_grid(s, s->dem, dem);
+    if (rc) return rc;
+    s->have_dem = true;
+    return wdpm_upload_water(s, water);
+}
+
+int wdpm_upload_water(wdpm_solver* s, const void* water) {
+    if (!s) return fail(WDPM_E_ARG, "null solver");
+    if (!s->have_dem) return fail(WDPM_E_STATE, "upload the DEM first");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (water) {
+        int rc = upload_grid(s, s->w[s->cur], water);
+        if (rc) return rc;
+    } else {
+        CUDA_TRY(cudaMemsetAsync(s->w[s->cur], 0, (size_t)s->g.cells_dev() * s->esize, s->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return WDPM_OK;
+}
+
+int wdpm_download_water(wdpm_solver* s, void* water) {
+    if (!s || !water) return fail(WDPM_E_ARG, "null argument");
+    if (!s->have_dem) return fail(WDPM_E_STATE, "nothing uploaded yet");
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaMemcpy2DAsync(water, (size_t)s->g.C * s->esize, interior_ptr(s, s->w[s->cur]), (size_t)s->g.pitch * s->esize,
+                               (size_t)s->g.C * s->esize, (size_t)s->g.R, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return WDPM_OK;
+}
+
+int wdpm_apply_add(wdpm_solver* s, double depth, double runoff_fraction) {
+    if (!s) return fail(WDPM_E_ARG, "null solver");
+    if (!s->have_dem) return fail(WDPM_E_STATE, "upload first");
+    CUDA_TRY(cudaSetDevice(s->device));
+    const long long n = (long long)s->g.R * s->g.C;
+    const int grid = grid_for(n, 256, s->sm_count);
+    if (s->dtype == WDPM_F64)
+        k_apply_add<double><<<grid, 256, 0, s->stream>>>(static_cast<double*>(s->w[s->cur]), static_cast<const double*>(s->dem), s->g,
+                                                         s->cfg.nodata, depth, depth * runoff_fraction);
+    else
+        k_apply_add<float><<<grid, 256, 0, s->stream>>>(static_cast<float*>(s->w[s->cur]), static_cast<const float*>(s->dem), s->g,
+                                                        (float)s->cfg.nodata, (float)depth, (float)(depth * runoff_fraction));
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return WDPM_OK;
+}
+
+int wdpm_apply_subtract(wdpm_solver* s, double depth) {
+    if (!s) return fail(WDPM_E_ARG, "null solver");
+    if (!s->have_dem) return fail(WDPM_E_STATE, "upload first");
+    CUDA_TRY(cudaSetDevice(s->device));
+    const long long n = (long long)s->g.R * s->g.C;
+    const int grid = grid_for(n, 256, s->sm_count);
+    if (s->dtype == WDPM_F64)
+        k_apply_subtract<double><<<grid, 256, 0, s->stream>>>(static_cast<double*>(s->w[s->cur]), static_cast<const double*>(s->dem),
+                                                              s->g, s->cfg.nodata, depth);
+    else
+        k_apply_subtract<float><<<grid, 256, 0, s->stream>>>(static_cast<float*>(s->w[s->cur]), static_cast<const float*>(s->dem), s->g,
+                                                             (float)s->cfg.nodata, (float)depth);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return WDPM_OK;
+}
+
+int wdpm_find_outlet(wdpm_solver* s, int32_t* drainrow, int32_t* draincol, double* min_elevation) {
+    if (!s) return fail(WDPM_E_ARG, "null solver");
+    if (!s->have_dem) return fail(WDPM_E_STATE, "upload first");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (s->dtype == WDPM_F64)
+        k_find_outlet_stage1<double, 256><<<s->reduce_blocks, 256, 0, s->stream>>>(static_cast<const double*>(s->dem), s->g, s->outlet_partials);
+    else
+        k_find_outlet_stage1<float, 256><<<s->reduce_blocks, 256, 0, s->stream>>>(static_cast<const float*>(s->dem), s->g, s->outlet_partials);
+    k_find_outlet_stage2<<<1, 32, 0, s->stream>>>(s->outlet_partials, s->reduce_blocks, s->d_outlet);
+    s->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    OutletCand c;
+    CUDA_TRY(cudaMemcpyAsync(&c, s->d_outlet, sizeof(c), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (c.index < 0) return fail(WDPM_E_STATE, "no cell with elevation > 0: no outlet");
+    s->drainrow = (int)(c.index / (s->g.C + 2));
+    s->draincol = (int)(c.index % (s->g.C + 2));
+    if (drainrow) *drainrow = s->drainrow;
+    if (draincol) *draincol = s->draincol;
+    if (min_elevation) *min_elevation = c.elev;
+    return WDPM_OK;
+}
+
+int wdpm_set_outlet(wdpm_solver* s, int32_t drainrow, int32_t draincol) {
+    if (!s) return fail(WDPM_E_ARG, "null solver");
+    if (drainrow < 0 || drainrow > s->g.R + 1 || draincol < 0 || draincol > s->g.C + 1) return fail(WDPM_E_ARG, "outlet outside the padded grid");
+    s->drainrow = drainrow;
+    s->draincol = draincol;
+    return WDPM_OK;
+}
+
+int wdpm_set_total_drain(wdpm_solver* s, double value) {
+    if (!s) return fail(WDPM_E_ARG, "null solver");
+    CUDA_TRY(cudaSetDevice(s->device));
+    double v64 = value;
+    float v32 = (float)value;
+    CUDA_TRY(cudaMemcpyAsync(s->totaldrain, s->dtype == WDPM_F64 ? (void*)&v64 : (void*)&v32, s->esize, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return WDPM_OK;
+}
+
+int wdpm_get_total_drain(wdpm_solver* s, double* value) {
+    if (!s || !value) return fail(WDPM_E_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    double v64 = 0;
+    float v32 = 0;
+    CUDA_TRY(cudaMemcpyAsync(s->dtype == WDPM_F64 ? (void*)&v64 : (void*)&v32, s->totaldrain, s->esize, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    *value = s->dtype == WDPM_F64 ? v64 : (double)v32;
+    return WDPM_OK;
+}
+
+int wdpm_get_cell_water(wdpm_solver* s, int32_t row, int32_t col, double* value) {
+    if (!s || !value) return fail(WDPM_E_ARG, "null argument");
+    if (row < 0 || row > s->g.R + 1 || col < 0 || col > s->g.C + 1) return fail(WDPM_E_ARG, "cell outside the padded grid");
+    CUDA_TRY(cudaSetDevice(s->device));
+    const size_t off = ((size_t)(row + kPadTop) * s->g.pitch + (size_t)(col + kPadLeft)) * s->esize;
+    double v64 = 0;
+    float v32 = 0;
+    CUDA_TRY(cudaMemcpyAsync(s->dtype == WDPM_F64 ? (void*)&v64 : (void*)&v32, static_cast<char*>(s->w[s->cur]) + off, s->esize,
+                             cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    *value = s->dtype == WDPM_F64 ? v64 : (double)v32;
+    return WDPM_OK;
+}
+
+int wdpm_run_block(wdpm_solver* s, int32_t n_iters, wdpm_block_result* out) {
+    if (!s) return fail(WDPM_E_ARG, "null solver");
+    if (n_iters < 0) return fail(WDPM_E_ARG, "negative iteration count");
+    if (!s->have_dem) return fail(WDPM_E_STATE, "upload first");
+    if (s->module == WDPM_DRAIN && s->drainrow < 0) return fail(WDPM_E_STATE, "Drain needs an outlet: call wdpm_find_outlet or wdpm_set_outlet");
+    CUDA_TRY(cudaSetDevice(s->device));
+    return s->dtype == WDPM_F64 ? run_block_t<double>(s, n_iters, out) : run_block_t<float>(s, n_iters, out);
+}
+
+int wdpm_iterate(wdpm_solver* s, int32_t n_iters) {
+    if (!s) return fail(WDPM_E_ARG, "null solver");
+    if (n_iters < 0) return fail(WDPM_E_ARG, "negative iteration count");
+    if (!s->have_dem) return fail(WDPM_E_STATE, "upload first");
+    if (s->module == WDPM_DRAIN && s->drainrow < 0) return fail(WDPM_E_STATE, "Drain needs an outlet");
+    CUDA_TRY(cudaSetDevice(s->device));
+    return iterate(s, n_iters);
+}
+
+int wdpm_subpass(wdpm_solver* s, int32_t oi, int32_t oj) {
+    if (!s) return fail(WDPM_E_ARG, "null solver");
+    if (oi < 1 || oi > 3 || oj < 1 || oj > 3) return fail(WDPM_E_ARG, "oi and oj must be 1..3");
+    if (!s->have_dem) return fail(WDPM_E_STATE, "upload first");
+    CUDA_TRY(cudaSetDevice(s->device));
+    return s->dtype == WDPM_F64 ? colour_subpass<double>(s, oi, oj) : colour_subpass<float>(s, oi, oj);
+}
+
+int wdpm_get_info(wdpm_solver* s, wdpm_info* info) {
+    if (!s || !info) return fail(WDPM_E_ARG, "null argument");
+    std::memset(info, 0, sizeof(*info));
+    info->device_bytes = s->device_bytes;
+    info->kernel_launches = s->launches;
+    info->kernel = s->kernel;
+    info->sm_count = s->sm_count;
+    int W, TWV, K, nt; size_t smem;
+    if (s->dtype == WDPM_F64) { const auto& v = fused_variants<double>()[s->variant]; W = v.W; TWV = v.TWV; K = v.K; nt = v.nthreads; smem = v.smem; }
+    else { const auto& v = fused_variants<float>()[s->variant]; W = v.W; TWV = v.TWV; K = v.K; nt = v.nthreads; smem = v.smem; }
+    info->strip_cols = TWV;
+    info->window_cols = W;
+    info->chunk_rows = 3 * s->chunk_triples;
+    info->grid_ctas = s->n_strips * s->n_chunks;
+    info->cta_threads = nt;
+    info->smem_bytes = (int32_t)smem;
+    info->iters_per_launch = s->kernel == WDPM_KERNEL_FUSED ? K : 1;
+    return WDPM_OK;
+}
+
+int wdpm_stripe_export(wdpm_solver* s, wdpm_stripe_endpoint* self) {
+    (void)s; (void)self;
+    return fail(WDPM_E_UNSUPPORTED, "row-stripe solvers are not implemented in this build");
+}
+
+int wdpm_stripe_connect(wdpm_solver* s, const wdpm_stripe_endpoint* above, const wdpm_stripe_endpoint* below) {
+    (void)s; (void)above; (void)below;
+    return fail(WDPM_E_UNSUPPORTED, "row-stripe solvers are not implemented in this build");
+}
+
+}  // extern "C"
