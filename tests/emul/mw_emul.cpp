@@ -102,7 +102,7 @@ void run_cta(const Layout& L, const T* w_in, T* w_out, const T* dem, T nodata, i
                     if (orow >= -1 && orow <= 1 && ocol >= -1 && ocol <= 1) {
                         if (orow == 0 && ocol == 0) continue;
                         T evo, evc; bool drained;
-                        relax_tile_at_outlet<T>(w0, w1, w2, d0, d1, d2, j, nodata, orow, ocol, &evo, &evc, &drained);
+                        relax_tile_at_outlet<T>(w0, w1, w2, d0, d1, d2, j, orow, ocol, &evo, &evc, &drained);
                         if (drained && tile.owns_row(crow) && tile.owns_col(ccol)) {
                             Event<T>& e = events[(ph / 3) * 9 + q * 3 + cofs];
                             e.w_outlet = evo; e.w_centre = evc; e.valid = 1;
@@ -110,7 +110,7 @@ void run_cta(const Layout& L, const T* w_in, T* w_out, const T* dem, T nodata, i
                         continue;
                     }
                 }
-                relax_tile<T, MODULE>(w0, w1, w2, d0, d1, d2, j, nodata);
+                relax_tile<T, MODULE>(w0, w1, w2, d0, d1, d2, j);
             }
         }
         std::vector<int> grp;
@@ -149,10 +149,10 @@ int run_launches(T* w_padded, const T* d_padded, int R, int C, T nodata, int n_l
     if (chunk_triples <= 0) chunk_triples = total_triples;
     const int n_chunks = (total_triples + chunk_triples - 1) / chunk_triples;
     const size_t n = (size_t)L.pitch * L.nrows_dev;
-    std::vector<T> dem(n, nodata), wa(n, T(0)), wb(n, T(0));
+    std::vector<T> dem(n, invalid_elevation<T>()), wa(n, T(0)), wb(n, T(0));  // masked elevations, as the solver stores them
     for (int i = 0; i < R + 2; i++)
         for (int j = 0; j < C + 2; j++) {
-            dem[L.at(i, j)] = d_padded[(size_t)i * (C + 2) + j];
+            dem[L.at(i, j)] = mask_elevation(d_padded[(size_t)i * (C + 2) + j], nodata);
             wa[L.at(i, j)] = w_padded[(size_t)i * (C + 2) + j];
         }
     Errors err;

@@ -5,7 +5,8 @@
 // (i, j) - the reference's bigdem[i][j] / bigwater[i][j], i in [0,R+1],
 // j in [0,C+1] (src/WDPMCL.c:795-807) - lives at
 //     (i + kPadTop) * pitch + (j + kPadLeft).
-// Everything outside the (R+2)x(C+2) padded grid is margin: dem = nodata,
+// Elevations are stored MASKED (relax.cuh): a cell with dem <= nodata holds +inf.
+// Everything outside the (R+2)x(C+2) padded grid is margin: dem = +inf,
 // water = 0. A margin cell can never become a centre (dry) nor receive water
 // (invalid neighbour), so kernels may compute on margins freely; this replaces
 // the reference's row/col range guard (src/runoff.cl:145).
@@ -40,33 +41,25 @@ __global__ void k_fill(T* __restrict__ a, long long n, T v) {
         a[i] = v;
 }
 
-// Copy an unpadded device staging array (R x C) into the padded device layout.
+// Mask the freshly uploaded interior of the DEM in place: dem <= nodata -> +inf (relax.cuh).
 template <typename T>
-__global__ void k_scatter_interior(T* __restrict__ dst, const T* __restrict__ src, Geom g) {
+__global__ void k_mask_dem(T* __restrict__ d, Geom g, T nodata) {
     const long long n = (long long)g.R * g.C;
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(k / g.C), j = (int)(k - (long long)i * g.C);
-        dst[dev_index(g, i + 1, j + 1)] = src[k];
-    }
-}
-
-template <typename T>
-__global__ void k_gather_interior(T* __restrict__ dst, const T* __restrict__ src, Geom g) {
-    const long long n = (long long)g.R * g.C;
-    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(k / g.C), j = (int)(k - (long long)i * g.C);
-        dst[k] = src[dev_index(g, i + 1, j + 1)];
+        const size_t a = dev_index(g, i + 1, j + 1);
+        d[a] = mask_elevation(d[a], nodata);
     }
 }
 
 // Add-module initial condition, valid cells only (src/WDPMCL.c:778-792).
 template <typename T>
-__global__ void k_apply_add(T* __restrict__ w, const T* __restrict__ d, Geom g, T nodata, T depth, T depth_rof) {
+__global__ void k_apply_add(T* __restrict__ w, const T* __restrict__ d, Geom g, T depth, T depth_rof) {
     const long long n = (long long)g.R * g.C;
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(k / g.C), j = (int)(k - (long long)i * g.C);
         const size_t a = dev_index(g, i + 1, j + 1);
-        if (d[a] > nodata) {
+        if (is_valid_elevation(d[a])) {
             T v = w[a];
             if (v > T(0)) v += depth;
             if (v <= T(0)) v = depth_rof;
@@ -78,12 +71,12 @@ __global__ void k_apply_add(T* __restrict__ w, const T* __restrict__ d, Geom g, 
 // Subtract-module initial condition (src/WDPMCL.c:919-926): max(w - depth, 0) with the
 // host macro's tie rule (a > b ? a : b).
 template <typename T>
-__global__ void k_apply_subtract(T* __restrict__ w, const T* __restrict__ d, Geom g, T nodata, T depth) {
+__global__ void k_apply_subtract(T* __restrict__ w, const T* __restrict__ d, Geom g, T depth) {
     const long long n = (long long)g.R * g.C;
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(k / g.C), j = (int)(k - (long long)i * g.C);
         const size_t a = dev_index(g, i + 1, j + 1);
-        if (d[a] > nodata) {
+        if (is_valid_elevation(d[a])) {
             const T v = w[a] - depth;
             w[a] = (v > T(0)) ? v : T(0);
         }
@@ -112,21 +105,28 @@ struct BlockPartial {
     unsigned long long wet;
 };
 
+// Stage 1 walks the PADDED grid (not the device array), block b taking rows b, b+grid, ... and
+// thread t columns t, t+NTHREADS, ...: the partial sums - hence the rounded total - depend only on
+// (R, C, grid size), not on the kernel variant's pitch or margins.
 template <typename T, int NTHREADS>
 __global__ void __launch_bounds__(NTHREADS)
 k_block_reduce_stage1(const T* __restrict__ w, const T* __restrict__ oldw, const T* __restrict__ d,
-                      long long n, T nodata, BlockPartial* __restrict__ partials) {
+                      Geom g, BlockPartial* __restrict__ partials) {
     T md = T(0);
     double sum = 0.0;
     unsigned long long wet = 0;
-    for (long long i = blockIdx.x * (long long)NTHREADS + threadIdx.x; i < n; i += (long long)gridDim.x * NTHREADS) {
-        if (d[i] > nodata) {
-            const T v = w[i];
-            T df = v - oldw[i];
-            df = df < T(0) ? -df : df;
-            md = df > md ? df : md;
-            sum += (double)v;
-            wet += (v > T(0)) ? 1ull : 0ull;
+    for (int i = blockIdx.x; i < g.R + 2; i += gridDim.x) {
+        const size_t base = dev_index(g, i, 0);
+        for (int j = threadIdx.x; j < g.C + 2; j += NTHREADS) {
+            const size_t a = base + j;
+            if (is_valid_elevation(d[a])) {
+                const T v = w[a];
+                T df = v - oldw[a];
+                df = df < T(0) ? -df : df;
+                md = df > md ? df : md;
+                sum += (double)v;
+                wet += (v > T(0)) ? 1ull : 0ull;
+            }
         }
     }
     double mdd = (double)md;
@@ -262,7 +262,7 @@ __global__ void k_fold_events(DrainState<T> ds, int parity) {
 
 template <typename T, int MODULE>
 __global__ void __launch_bounds__(256)
-k_colour(T* __restrict__ w, const T* __restrict__ d, Geom g, T nodata, int oi, int oj, DrainState<T> ds) {
+k_colour(T* __restrict__ w, const T* __restrict__ d, Geom g, int oi, int oj, DrainState<T> ds) {
     const int gx = blockIdx.x * blockDim.x + threadIdx.x;
     const int gy = blockIdx.y * blockDim.y + threadIdx.y;
     const int row = oi + 3 * gy, col = oj + 3 * gx;
@@ -276,7 +276,7 @@ k_colour(T* __restrict__ w, const T* __restrict__ d, Geom g, T nodata, int oi, i
             if (orow == 0 && ocol == 0) return;  // the outlet is never a centre (src/runoff.cl:179)
             T evo, evc;
             bool drained;
-            relax_tile_at_outlet<T>(w1 - g.pitch, w1, w1 + g.pitch, d1 - g.pitch, d1, d1 + g.pitch, 0, nodata,
+            relax_tile_at_outlet<T>(w1 - g.pitch, w1, w1 + g.pitch, d1 - g.pitch, d1, d1 + g.pitch, 0,
                                     orow, ocol, &evo, &evc, &drained);
             if (drained) {  // single writer per sub-pass
                 T td = *ds.totaldrain;
@@ -287,7 +287,7 @@ k_colour(T* __restrict__ w, const T* __restrict__ d, Geom g, T nodata, int oi, i
             return;
         }
     }
-    relax_tile<T, MODULE>(w1 - g.pitch, w1, w1 + g.pitch, d1 - g.pitch, d1, d1 + g.pitch, 0, nodata);
+    relax_tile<T, MODULE>(w1 - g.pitch, w1, w1 + g.pitch, d1 - g.pitch, d1, d1 + g.pitch, 0);
 }
 
 // ---------------------------------------------------------------------------
@@ -335,7 +335,6 @@ struct FusedParams {
     T* w_out;
     const T* dem;
     Geom g;
-    T nodata;
     int n_strips;
     int chunk_triples;  // owned row triples per CTA
     int total_triples;  // ceil((R+2)/3)
@@ -404,49 +403,84 @@ k_fused(const FusedParams<T> p) {
         for (int s = 0; s < PF && s < tile.n_steps; s++) issue_loads(s);
     }
 
+    // Static work assignment: in every sub-step thread `tid` relaxes tiles number tid,
+    // tid+NTHREADS, ... of the NPH*NT*NC tiles (phase-major, then triple slot, then column), so its
+    // phase / triple slot / column never change and are decoded once.
+    constexpr int NC = CFG::NC;
+    constexpr int NITEMS = NPH * NT * NC;
+    constexpr int IPT = (NITEMS + NTHREADS - 1) / NTHREADS;
+    int it_col[IPT], it_q[IPT], it_ph[IPT], it_mrel[IPT];
+    bool it_ok[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        const int item = tid + k * NTHREADS;
+        it_ok[k] = item < NITEMS;
+        const int c = item % NC, pt = item / NC, t = pt % NT, ph = pt / NT;
+        it_col[k] = 3 * c + 1;
+        it_ph[k] = ph;
+        it_q[k] = ph % 3;
+        it_mrel[k] = t - ph * CFG::LAG;
+    }
+
     for (int s = 0; s < tile.n_steps; s++) {
         // issue the prefetch for step s+PF: its ring slots were released at the end of step s-1
         if (tid == 0 && s + PF < tile.n_steps) issue_loads(s + PF);
         if (step_has_loads(s)) mbar_wait(&bars[s % NSTAGE], (uint32_t)((s / NSTAGE) & 1));
 
+        bool run[IPT];
+        int row0[IPT];
+        T* wrow[IPT][3];
+#pragma unroll
+        for (int k = 0; k < IPT; k++) {
+            const int m = tile.m_lo + NT * s + it_mrel[k];
+            run[k] = it_ok[k] && tile.runnable(m, it_q[k]);
+            row0[k] = 3 * m + it_q[k];
+            int s0 = run[k] ? tile.ring_slot(row0[k]) : 0;
+            int s1 = s0 + 1; if (s1 == NRING) s1 = 0;
+            int s2 = s1 + 1; if (s2 == NRING) s2 = 0;
+            wrow[k][0] = ring_w + s0 * W; wrow[k][1] = ring_w + s1 * W; wrow[k][2] = ring_w + s2 * W;
+        }
+        constexpr int DOFF = NRING * W;  // ring_d = ring_w + DOFF
+
 #pragma unroll 1
         for (int cofs = 0; cofs < 3; cofs++) {
-            constexpr int nc = CFG::NC;
-            constexpr int nitems = NPH * NT * nc;
-            for (int item = tid; item < nitems; item += NTHREADS) {
-                const int c = item % nc;
-                const int pt = item / nc;
-                const int t = pt % NT;
-                const int ph = pt / NT;
-                const int q = ph % 3;
-                const int m = tile.triple(s, ph, t);
-                if (!tile.runnable(m, q)) continue;
-                const int row0 = 3 * m + q;
-                int s0 = tile.ring_slot(row0);
-                int s1 = s0 + 1; if (s1 == NRING) s1 = 0;
-                int s2 = s1 + 1; if (s2 == NRING) s2 = 0;
-                const int j = 3 * c + cofs + 1;  // centre column inside the window
-                T* w0 = ring_w + s0 * W; T* w1 = ring_w + s1 * W; T* w2 = ring_w + s2 * W;
-                const T* d0 = ring_d + s0 * W; const T* d1 = ring_d + s1 * W; const T* d2 = ring_d + s2 * W;
-                if (MODULE == kDrain) {
-                    const int crow = row0 + 1, ccol = tile.x0 + j;
-                    const int orow = p.ds.drainrow - crow, ocol = p.ds.draincol - ccol;
-                    if (orow >= -1 && orow <= 1 && ocol >= -1 && ocol <= 1) {
-                        if (orow == 0 && ocol == 0) continue;
-                        T evo, evc;
-                        bool drained;
-                        relax_tile_at_outlet<T>(w0, w1, w2, d0, d1, d2, j, p.nodata, orow, ocol, &evo, &evc, &drained);
-                        // only the CTA that owns the centre reports the event (halo copies recompute it)
-                        if (drained && tile.owns_row(crow) && tile.owns_col(ccol)) {
-                            DrainEvent<T>* ev = p.ds.events + p.launch_parity * kEventsPerBuffer + (ph / 3) * 9 + q * 3 + cofs;
-                            ev->w_outlet = evo;
-                            ev->w_centre = evc;
-                            ev->valid = 1;
+            Tile<T> tl[IPT];
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < IPT; k++) {
+                const int j = it_col[k] + cofs;  // centre column inside the window
+                tl[k].active = false;
+                if (run[k]) {
+                    if (MODULE == kDrain) {
+                        const int crow = row0[k] + 1, ccol = tile.x0 + j;
+                        const int orow = p.ds.drainrow - crow, ocol = p.ds.draincol - ccol;
+                        if (orow >= -1 && orow <= 1 && ocol >= -1 && ocol <= 1) {
+                            if (orow != 0 || ocol != 0) {
+                                T evo, evc;
+                                bool drained;
+                                relax_tile_at_outlet<T>(wrow[k][0], wrow[k][1], wrow[k][2], wrow[k][0] + DOFF, wrow[k][1] + DOFF,
+                                                        wrow[k][2] + DOFF, j, orow, ocol, &evo, &evc, &drained);
+                                // only the CTA that owns the centre reports the event (halo copies recompute it)
+                                if (drained && tile.owns_row(crow) && tile.owns_col(ccol)) {
+                                    DrainEvent<T>* ev = p.ds.events + p.launch_parity * kEventsPerBuffer + (it_ph[k] / 3) * 9 + it_q[k] * 3 + cofs;
+                                    ev->w_outlet = evo;
+                                    ev->w_centre = evc;
+                                    ev->valid = 1;
+                                }
+                            }
+                            continue;
                         }
-                        continue;
                     }
+                    tile_load(tl[k], wrow[k][0], wrow[k][1], wrow[k][2], wrow[k][0] + DOFF, wrow[k][1] + DOFF, wrow[k][2] + DOFF, j);
+                    any = any || tl[k].active;
                 }
-                relax_tile<T, MODULE>(w0, w1, w2, d0, d1, d2, j, p.nodata);
+            }
+            if (any) {
+                // inactive tiles of this thread ride along on dead values; they are not stored
+                tiles_relax<T, MODULE, IPT>(tl);
+#pragma unroll
+                for (int k = 0; k < IPT; k++)
+                    if (tl[k].active) tile_store(tl[k], wrow[k][0], wrow[k][1], wrow[k][2], it_col[k] + cofs);
             }
             if (cofs == 2) fence_proxy_async();  // make this step's smem writes visible to the bulk-store engine
             __syncthreads();

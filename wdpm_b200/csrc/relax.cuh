@@ -6,25 +6,32 @@
 //   DRAIN     src/runoff.cl:90-134  (runoffdrain)
 // with the centre guard of src/runoff.cl:145 / :160 / :177-179.
 //
-// The functions are written against three water rows and three elevation rows
-// (any address space: global memory for the colour kernel, the shared-memory row
-// ring for the fused kernel) and a centre column index. They are __host__
-// __device__ so the schedule emulator in tests/ can run the very same arithmetic
-// on the CPU; the product never calls them on the host.
+// MASKED ELEVATIONS. The solver stores the DEM with every invalid cell
+// (dem <= nodata, i.e. NODATA cells, the halo ring and the device margins)
+// replaced by +infinity. A neighbour at +inf has surface sn = +inf, so the
+// height difference h = sc - sn is -inf and the `h > 0` test fails exactly
+// where the reference's `bigdem[n] > missingvalue` guard (runoff.cl:33) would
+// have skipped the neighbour: the validity compare and its branch disappear
+// from the inner loop. A centre is valid iff its elevation is finite.
+//
+// The step is written branch-free (selects / predicated adds) against a
+// register-resident tile so that several tiles can be relaxed interleaved by
+// one thread: the eight neighbour steps of a tile form one dependent chain,
+// and interleaving independent chains is what keeps the FP pipes busy.
+//
+// The functions are __host__ __device__ so the schedule emulator in tests/ can
+// run the very same arithmetic on the CPU; the product never calls them there.
 //
 // Arithmetic notes (each keeps the reference's result bit-identical):
 //  * x/8.0 is computed as x*0.125: scaling by a power of two is exact, and in the
-//    subnormal range both round the same exact quotient.
+//    subnormal range both round the same exact quotient. Selecting the operand
+//    first ((dc>sn ? wc : h) * 0.125) is the same operation on the same value.
 //  * runoffadd's maxi(flow,0) and maxi(w-flow,0) are dropped: there flow is
 //    w/8 or h/8 with w>0, h>0, so 0 <= flow, and mini(flow,w) <= w makes
 //    w-flow >= +0 exactly. runoffdrain's four-term flow can be <= 0, so its
-//    maxi(flow,0) stays (as a compare+select, which is what maxi is); its second
-//    clamp is a no-op for the same reason as above.
-//  * mini(a,b) = (a<=b)?a:b equals fmin(a,b) unless an operand is NaN or the
-//    operands are zeros of opposite sign; neither arises from finite inputs
-//    (see DESIGN.md "bit-exactness").
-//  * the file is compiled with -fmad=false; there is no multiply-add to contract
-//    anyway (only + - *0.125 min max compare).
+//    maxi(flow,0) stays; its second clamp is a no-op for the same reason.
+//  * mini(a,b) is written as the reference writes it, (a<=b)?a:b.
+//  * compiled with -fmad=false; there is no multiply-add to contract anyway.
 #pragma once
 
 #ifdef __CUDACC__
@@ -34,71 +41,104 @@
 #include <cmath>
 #endif
 
+#include <limits>
+
 namespace wdpm {
 
 enum : int { kAdd = 0, kSubtract = 1, kDrain = 2 };
 
 template <typename T>
-WDPM_HD T min_finite(T a, T b) {
+WDPM_HD T invalid_elevation() {
 #ifdef __CUDA_ARCH__
-    return fmin(a, b);
+    return sizeof(T) == 8 ? (T)__longlong_as_double(0x7ff0000000000000LL) : (T)__int_as_float(0x7f800000);
 #else
-    return (a <= b) ? a : b;
+    return std::numeric_limits<T>::infinity();
 #endif
 }
+template <typename T>
+WDPM_HD bool is_valid_elevation(T d) { return d < invalid_elevation<T>(); }
+// what the upload path stores for a raw elevation
+template <typename T>
+WDPM_HD T mask_elevation(T d, T nodata) { return (d > nodata) ? d : invalid_elevation<T>(); }
 
-// One neighbour step. wc is the centre's running water, (dn, wn) the neighbour.
+// A 3x3 tile held in registers. Neighbour order: row offset outer, column
+// offset inner (src/runoff.cl:28-30): 0 1 2 / 3 c 4 / 5 6 7.
+template <typename T>
+struct Tile {
+    T wc, dc;
+    T wn[8], dn[8];
+    bool active;  // centre wet and valid: the reference would have called runoff*()
+};
+
+template <typename T>
+WDPM_HD void tile_load(Tile<T>& t, const T* w0, const T* w1, const T* w2, const T* d0, const T* d1, const T* d2, int j) {
+    t.wc = w1[j];
+    t.dc = d1[j];
+    t.active = (t.wc > T(0)) && is_valid_elevation(t.dc);
+    t.wn[0] = w0[j - 1]; t.wn[1] = w0[j]; t.wn[2] = w0[j + 1];
+    t.wn[3] = w1[j - 1]; t.wn[4] = w1[j + 1];
+    t.wn[5] = w2[j - 1]; t.wn[6] = w2[j]; t.wn[7] = w2[j + 1];
+    t.dn[0] = d0[j - 1]; t.dn[1] = d0[j]; t.dn[2] = d0[j + 1];
+    t.dn[3] = d1[j - 1]; t.dn[4] = d1[j + 1];
+    t.dn[5] = d2[j - 1]; t.dn[6] = d2[j]; t.dn[7] = d2[j + 1];
+}
+
+template <typename T>
+WDPM_HD void tile_store(const Tile<T>& t, T* w0, T* w1, T* w2, int j) {
+    w0[j - 1] = t.wn[0]; w0[j] = t.wn[1]; w0[j + 1] = t.wn[2];
+    w1[j - 1] = t.wn[3]; w1[j] = t.wc;    w1[j + 1] = t.wn[4];
+    w2[j - 1] = t.wn[5]; w2[j] = t.wn[6]; w2[j + 1] = t.wn[7];
+}
+
+// One neighbour step, branch-free. wc is the centre's running water.
 template <typename T, int MODULE>
-WDPM_HD void push(T dc, T& wc, T dn, T& wn, T nodata) {
-    if (dn > nodata) {
-        const T sn = dn + wn;
-        const T sc = dc + wc;
-        const T h = sc - sn;
-        if (h > T(0)) {
-            T flow;
-            if (MODULE == kAdd) {
-                flow = (dc > sn) ? wc * T(0.125) : h * T(0.125);
-                flow = min_finite(flow, wc);
-            } else {
-                flow = (dc > sn) ? wc * T(0.125) : ((dc - dn) + (wc - wn)) * T(0.125);
-                if (MODULE == kDrain) flow = (flow <= T(0)) ? T(0) : flow;
-                flow = min_finite(flow, wc);
-            }
-            wc = wc - flow;
-            wn = wn + flow;
-        }
+WDPM_HD void push(T dc, T& wc, T dn, T& wn) {
+    const T sn = dn + wn;
+    const T sc = dc + wc;
+    const T h = sc - sn;
+    const bool pos = h > T(0);
+    T x;
+    if (MODULE == kAdd) x = (dc > sn) ? wc : h;
+    else x = (dc > sn) ? wc : ((dc - dn) + (wc - wn));
+    T flow = x * T(0.125);
+    if (MODULE == kDrain) flow = (flow <= T(0)) ? T(0) : flow;
+    flow = (flow <= wc) ? flow : wc;
+    wc = pos ? wc - flow : wc;
+    wn = pos ? wn + flow : wn;
+}
+
+// The eight neighbour steps of one tile (only meaningful when t.active).
+template <typename T, int MODULE>
+WDPM_HD void tile_relax(Tile<T>& t) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int n = 0; n < 8; n++) push<T, MODULE>(t.dc, t.wc, t.dn[n], t.wn[n]);
+}
+
+// N independent tiles, neighbour step by neighbour step, so the compiler
+// interleaves the N dependent chains.
+template <typename T, int MODULE, int N>
+WDPM_HD void tiles_relax(Tile<T> (&t)[N]) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int n = 0; n < 8; n++) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int k = 0; k < N; k++) push<T, MODULE>(t[k].dc, t[k].wc, t[k].dn[n], t[k].wn[n]);
     }
 }
 
-// Relax the tile centred at column j of rows (w0,w1,w2)/(d0,d1,d2).
-// Returns true if the centre was wet and valid (work was done).
+// Convenience: load, relax if active, store. Returns whether work was done.
 template <typename T, int MODULE>
-WDPM_HD bool relax_tile(T* w0, T* w1, T* w2, const T* d0, const T* d1, const T* d2, int j, T nodata) {
-    T wc = w1[j];
-    if (!(wc > T(0))) return false;
-    const T dc = d1[j];
-    if (!(dc > nodata)) return false;
-
-    T wn0 = w0[j - 1], wn1 = w0[j], wn2 = w0[j + 1];
-    T wn3 = w1[j - 1], wn4 = w1[j + 1];
-    T wn5 = w2[j - 1], wn6 = w2[j], wn7 = w2[j + 1];
-    const T dn0 = d0[j - 1], dn1 = d0[j], dn2 = d0[j + 1];
-    const T dn3 = d1[j - 1], dn4 = d1[j + 1];
-    const T dn5 = d2[j - 1], dn6 = d2[j], dn7 = d2[j + 1];
-
-    // neighbour order: row offset outer, column offset inner (src/runoff.cl:28-30)
-    push<T, MODULE>(dc, wc, dn0, wn0, nodata);
-    push<T, MODULE>(dc, wc, dn1, wn1, nodata);
-    push<T, MODULE>(dc, wc, dn2, wn2, nodata);
-    push<T, MODULE>(dc, wc, dn3, wn3, nodata);
-    push<T, MODULE>(dc, wc, dn4, wn4, nodata);
-    push<T, MODULE>(dc, wc, dn5, wn5, nodata);
-    push<T, MODULE>(dc, wc, dn6, wn6, nodata);
-    push<T, MODULE>(dc, wc, dn7, wn7, nodata);
-
-    w0[j - 1] = wn0; w0[j] = wn1; w0[j + 1] = wn2;
-    w1[j - 1] = wn3; w1[j] = wc;  w1[j + 1] = wn4;
-    w2[j - 1] = wn5; w2[j] = wn6; w2[j + 1] = wn7;
+WDPM_HD bool relax_tile(T* w0, T* w1, T* w2, const T* d0, const T* d1, const T* d2, int j) {
+    Tile<T> t;
+    tile_load(t, w0, w1, w2, d0, d1, d2, j);
+    if (!t.active) return false;
+    tile_relax<T, MODULE>(t);
+    tile_store(t, w0, w1, w2, j);
     return true;
 }
 
@@ -110,19 +150,19 @@ WDPM_HD bool relax_tile(T* w0, T* w1, T* w2, const T* d0, const T* d1, const T* 
 // sub-pass order: *ev_outlet = w[outlet], *ev_centre = w[centre] at that moment.
 template <typename T>
 WDPM_HD bool relax_tile_at_outlet(T* w0, T* w1, T* w2, const T* d0, const T* d1, const T* d2, int j,
-                                  T nodata, int orow, int ocol, T* ev_outlet, T* ev_centre, bool* drained) {
+                                  int orow, int ocol, T* ev_outlet, T* ev_centre, bool* drained) {
     *drained = false;
     T wc = w1[j];
     if (!(wc > T(0))) return false;
     const T dc = d1[j];
-    if (!(dc > nodata)) return false;
+    if (!is_valid_elevation(dc)) return false;
     T* wr[3] = {w0, w1, w2};
     const T* dr[3] = {d0, d1, d2};
     for (int a = -1; a <= 1; a++) {
         for (int b = -1; b <= 1; b++) {
             if (a == 0 && b == 0) continue;
             const T dn = dr[a + 1][j + b];
-            if (!(dn > nodata)) continue;
+            if (!is_valid_elevation(dn)) continue;
             T wn = wr[a + 1][j + b];
             if (a == orow && b == ocol) {
                 *ev_outlet = wn;
@@ -131,7 +171,7 @@ WDPM_HD bool relax_tile_at_outlet(T* w0, T* w1, T* w2, const T* d0, const T* d1,
                 wn = T(0);
                 wc = T(0);
             } else {
-                push<T, kDrain>(dc, wc, dn, wn, nodata);
+                push<T, kDrain>(dc, wc, dn, wn);
             }
             wr[a + 1][j + b] = wn;
         }

@@ -84,24 +84,32 @@ const std::vector<FusedVariant<T>>& fused_variants();
 template <>
 const std::vector<FusedVariant<double>>& fused_variants<double>() {
     static const std::vector<FusedVariant<double>> v = {
-        make_variant<double, MwCfg<512, 1, 1, 2>, 512, 1>(),  // 1: 192 KB ring, one CTA per SM
-        make_variant<double, MwCfg<64, 1, 1, 1>, 128, 1>(),   // 2: test
-        make_variant<double, MwCfg<128, 1, 2, 2>, 256, 1>(),  // 3: test, two iterations per launch
-        make_variant<double, MwCfg<320, 2, 1, 2>, 512, 1>(),  // 4: two triples per phase
-        make_variant<double, MwCfg<256, 1, 1, 2>, 256, 2>(),  // 5: two CTAs per SM
-        make_variant<double, MwCfg<256, 1, 2, 2>, 512, 1>(),  // 6: two iterations per launch
+        make_variant<double, MwCfg<512, 1, 1, 2>, 512, 1>(),   // 1: 192 KB ring, one CTA per SM, one tile per thread
+        make_variant<double, MwCfg<64, 1, 1, 1>, 128, 1>(),    // 2: test
+        make_variant<double, MwCfg<128, 1, 2, 2>, 128, 1>(),   // 3: test, two iterations per launch, two tiles per thread
+        make_variant<double, MwCfg<384, 2, 1, 1>, 512, 1>(),   // 4: two triples per phase, two tiles per thread
+        make_variant<double, MwCfg<256, 1, 1, 2>, 256, 2>(),   // 5: two CTAs per SM
+        make_variant<double, MwCfg<256, 1, 2, 2>, 512, 1>(),   // 6: two iterations per launch
+        make_variant<double, MwCfg<512, 1, 1, 2>, 256, 1>(),   // 7: as 1, two tiles per thread
+        make_variant<double, MwCfg<320, 2, 1, 2>, 1024, 1>(),  // 8: two triples per phase, 32 warps
+        make_variant<double, MwCfg<384, 2, 1, 1>, 256, 1>(),   // 9: two triples per phase, three tiles per thread
+        make_variant<double, MwCfg<384, 2, 1, 1>, 768, 1>(),   // 10: two triples per phase, 24 warps, one tile per thread
     };
     return v;
 }
 template <>
 const std::vector<FusedVariant<float>>& fused_variants<float>() {
     static const std::vector<FusedVariant<float>> v = {
-        make_variant<float, MwCfg<512, 1, 1, 2>, 256, 2>(),   // 1: 96 KB ring, two CTAs per SM
-        make_variant<float, MwCfg<64, 1, 1, 1>, 128, 1>(),    // 2: test
-        make_variant<float, MwCfg<128, 1, 2, 2>, 256, 1>(),   // 3: test, two iterations per launch
-        make_variant<float, MwCfg<384, 2, 1, 2>, 512, 1>(),   // 4
-        make_variant<float, MwCfg<1024, 1, 1, 2>, 512, 1>(),  // 5: wide window
-        make_variant<float, MwCfg<512, 1, 2, 2>, 512, 1>(),   // 6: two iterations per launch
+        make_variant<float, MwCfg<512, 1, 1, 2>, 256, 2>(),    // 1: 96 KB ring, two CTAs per SM, two tiles per thread
+        make_variant<float, MwCfg<64, 1, 1, 1>, 128, 1>(),     // 2: test
+        make_variant<float, MwCfg<128, 1, 2, 2>, 128, 1>(),    // 3: test, two iterations per launch
+        make_variant<float, MwCfg<384, 2, 1, 2>, 512, 1>(),    // 4
+        make_variant<float, MwCfg<1024, 1, 1, 2>, 512, 1>(),   // 5: wide window, two tiles per thread
+        make_variant<float, MwCfg<512, 1, 2, 2>, 512, 1>(),    // 6: two iterations per launch
+        make_variant<float, MwCfg<512, 1, 1, 2>, 512, 2>(),    // 7: as 1, one tile per thread
+        make_variant<float, MwCfg<768, 2, 1, 1>, 1024, 1>(),   // 8: two triples per phase, 32 warps
+        make_variant<float, MwCfg<768, 2, 1, 1>, 512, 1>(),    // 9: two triples per phase, three tiles per thread
+        make_variant<float, MwCfg<384, 2, 1, 1>, 768, 2>(),    // 10: two CTAs of 24 warps per SM
     };
     return v;
 }
@@ -174,12 +182,11 @@ int colour_subpass(wdpm_solver* s, int oi, int oj) {
     const dim3 grid((ncx + block.x - 1) / block.x, (ncy + block.y - 1) / block.y);
     T* w = static_cast<T*>(s->w[s->cur]);
     const T* d = static_cast<const T*>(s->dem);
-    const T nodata = (T)s->cfg.nodata;
     DrainState<T> ds = drain_state<T>(s);
     switch (s->module) {
-        case WDPM_ADD: k_colour<T, kAdd><<<grid, block, 0, s->stream>>>(w, d, s->g, nodata, oi, oj, ds); break;
-        case WDPM_SUBTRACT: k_colour<T, kSubtract><<<grid, block, 0, s->stream>>>(w, d, s->g, nodata, oi, oj, ds); break;
-        default: k_colour<T, kDrain><<<grid, block, 0, s->stream>>>(w, d, s->g, nodata, oi, oj, ds); break;
+        case WDPM_ADD: k_colour<T, kAdd><<<grid, block, 0, s->stream>>>(w, d, s->g, oi, oj, ds); break;
+        case WDPM_SUBTRACT: k_colour<T, kSubtract><<<grid, block, 0, s->stream>>>(w, d, s->g, oi, oj, ds); break;
+        default: k_colour<T, kDrain><<<grid, block, 0, s->stream>>>(w, d, s->g, oi, oj, ds); break;
     }
     s->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -207,7 +214,6 @@ int fused_iterations(wdpm_solver* s, int n) {
         p.w_out = static_cast<T*>(s->w[s->cur ^ 1]);
         p.dem = static_cast<const T*>(s->dem);
         p.g = s->g;
-        p.nodata = (T)s->cfg.nodata;
         p.n_strips = s->n_strips;
         p.chunk_triples = s->chunk_triples;
         p.total_triples = s->total_triples;
@@ -251,8 +257,7 @@ int run_block_t(wdpm_solver* s, int n_iters, wdpm_block_result* out) {
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
     k_block_reduce_stage1<T, 256><<<s->reduce_blocks, 256, 0, s->stream>>>(
-        static_cast<const T*>(s->w[s->cur]), static_cast<const T*>(s->oldw), static_cast<const T*>(s->dem), n,
-        (T)s->cfg.nodata, s->partials);
+        static_cast<const T*>(s->w[s->cur]), static_cast<const T*>(s->oldw), static_cast<const T*>(s->dem), s->g, s->partials);
     k_block_reduce_stage2<<<1, 32, 0, s->stream>>>(s->partials, s->reduce_blocks, s->d_result);
     s->launches += 2;
     CUDA_TRY(cudaGetLastError());
@@ -277,7 +282,7 @@ int run_block_t(wdpm_solver* s, int n_iters, wdpm_block_result* out) {
 template <typename T>
 int fill_dem(wdpm_solver* s) {
     const long long n = s->g.cells_dev();
-    k_fill<T><<<grid_for(n, 256, s->sm_count), 256, 0, s->stream>>>(static_cast<T*>(s->dem), n, (T)s->cfg.nodata);
+    k_fill<T><<<grid_for(n, 256, s->sm_count), 256, 0, s->stream>>>(static_cast<T*>(s->dem), n, invalid_elevation<T>());
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     return WDPM_OK;
@@ -509,6 +514,13 @@ int wdpm_upload(wdpm_solver* s, const void* dem, const void* water) {
     CUDA_TRY(cudaSetDevice(s->device));
     int rc = upload_grid(s, s->dem, dem);
     if (rc) return rc;
+    {   // store elevations masked: dem <= nodata -> +inf (relax.cuh)
+        const int grid = grid_for((long long)s->g.R * s->g.C, 256, s->sm_count);
+        if (s->dtype == WDPM_F64) k_mask_dem<double><<<grid, 256, 0, s->stream>>>(static_cast<double*>(s->dem), s->g, s->cfg.nodata);
+        else k_mask_dem<float><<<grid, 256, 0, s->stream>>>(static_cast<float*>(s->dem), s->g, (float)s->cfg.nodata);
+        s->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
     s->have_dem = true;
     return wdpm_upload_water(s, water);
 }
@@ -545,10 +557,10 @@ int wdpm_apply_add(wdpm_solver* s, double depth, double runoff_fraction) {
     const int grid = grid_for(n, 256, s->sm_count);
     if (s->dtype == WDPM_F64)
         k_apply_add<double><<<grid, 256, 0, s->stream>>>(static_cast<double*>(s->w[s->cur]), static_cast<const double*>(s->dem), s->g,
-                                                         s->cfg.nodata, depth, depth * runoff_fraction);
+                                                         depth, depth * runoff_fraction);
     else
         k_apply_add<float><<<grid, 256, 0, s->stream>>>(static_cast<float*>(s->w[s->cur]), static_cast<const float*>(s->dem), s->g,
-                                                        (float)s->cfg.nodata, (float)depth, (float)(depth * runoff_fraction));
+                                                        (float)depth, (float)(depth * runoff_fraction));
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     return WDPM_OK;
@@ -562,10 +574,10 @@ int wdpm_apply_subtract(wdpm_solver* s, double depth) {
     const int grid = grid_for(n, 256, s->sm_count);
     if (s->dtype == WDPM_F64)
         k_apply_subtract<double><<<grid, 256, 0, s->stream>>>(static_cast<double*>(s->w[s->cur]), static_cast<const double*>(s->dem),
-                                                              s->g, s->cfg.nodata, depth);
+                                                              s->g, depth);
     else
         k_apply_subtract<float><<<grid, 256, 0, s->stream>>>(static_cast<float*>(s->w[s->cur]), static_cast<const float*>(s->dem), s->g,
-                                                             (float)s->cfg.nodata, (float)depth);
+                                                             (float)depth);
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     return WDPM_OK;
