@@ -13,6 +13,7 @@
 #pragma once
 
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 #include "mw_schedule.h"
@@ -348,7 +349,7 @@ constexpr size_t fused_smem_bytes() {
 }
 
 template <typename T, int MODULE, typename CFG, int NTHREADS, int MINB>
-__global__ void __launch_bounds__(NTHREADS, MINB)
+__global__ void __launch_bounds__(NTHREADS + 32, MINB)
 k_fused(const FusedParams<T> p) {
     constexpr int W = CFG::W, NT = CFG::NT, NPH = CFG::NPH, NRING = CFG::NRING, NSTAGE = CFG::NSTAGE, PF = CFG::PF;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -399,8 +400,47 @@ k_fused(const FusedParams<T> p) {
         return false;
     };
 
-    if (tid == 0) {
-        for (int s = 0; s < PF && s < tile.n_steps; s++) issue_loads(s);
+    auto issue_stores = [&](int s) {  // rows finished by the last phase in step s: C-type rows 3m+2 .. 3m+4
+        bool any = false;
+        for (int t = 0; t < NT; t++) {
+            const int m = tile.triple(s, NPH - 1, t);
+            for (int k = 0; k < 3; k++) {
+                const int row = 3 * m + 2 + k;
+                if (!tile.owns_row(row)) continue;
+                const size_t dst = (size_t)(row + kPadTop) * (size_t)p.g.pitch + col0 + CFG::HL;
+                bulk_store(p.w_out + dst, ring_w + (size_t)tile.ring_slot(row) * W + CFG::HL, CFG::TWV * sizeof(T));
+                any = true;
+            }
+        }
+        if (any) bulk_commit();
+    };
+
+    // Warp specialisation: the last warp only moves data (one elected lane issues the bulk copies),
+    // the first NTHREADS threads only compute. Both sides meet at the three block barriers of a step.
+    if (tid >= NTHREADS) {
+        const bool lead = tid == NTHREADS;
+        if (lead)
+            for (int s = 0; s < PF && s < tile.n_steps; s++) issue_loads(s);
+        for (int s = 0; s < tile.n_steps; s++) {
+            if (lead) {
+                if (s > 0) {
+                    issue_stores(s - 1);
+                    // ring slots reused by the next prefetch must have been read out by their stores:
+                    // only the group committed just now may still be in flight
+                    bulk_wait_read<1>();
+                }
+                if (s + PF < tile.n_steps) issue_loads(s + PF);
+            }
+            __syncwarp();
+            __syncthreads();
+            __syncthreads();
+            __syncthreads();
+        }
+        if (lead) {
+            issue_stores(tile.n_steps - 1);
+            bulk_wait_read<0>();
+        }
+        return;
     }
 
     // Static work assignment: in every sub-step thread `tid` relaxes tiles number tid,
@@ -423,13 +463,19 @@ k_fused(const FusedParams<T> p) {
     }
 
     for (int s = 0; s < tile.n_steps; s++) {
-        // issue the prefetch for step s+PF: its ring slots were released at the end of step s-1
-        if (tid == 0 && s + PF < tile.n_steps) issue_loads(s + PF);
         if (step_has_loads(s)) mbar_wait(&bars[s % NSTAGE], (uint32_t)((s / NSTAGE) & 1));
 
-        bool run[IPT];
+        // Per tile: the three ring rows it spans this step, and a register window that slides one
+        // column per colour sub-pass. wt = 3x3 water (rows x cols jb-1+cofs .. jb+1+cofs), dd = the
+        // 3x5 elevations under all three positions. Between sub-passes only the column that leaves
+        // the window is written to shared memory (the left-hand tile needs it next) and only the
+        // column that enters is read (the right-hand tile has just published it); after the third
+        // sub-pass the whole window is written back.
+        bool run[IPT], slow[IPT], dirty[IPT];
         int row0[IPT];
         T* wrow[IPT][3];
+        T wt[IPT][3][3], dd[IPT][3][5];
+        constexpr int DOFF = NRING * W;  // ring_d = ring_w + DOFF
 #pragma unroll
         for (int k = 0; k < IPT; k++) {
             const int m = tile.m_lo + NT * s + it_mrel[k];
@@ -439,75 +485,89 @@ k_fused(const FusedParams<T> p) {
             int s1 = s0 + 1; if (s1 == NRING) s1 = 0;
             int s2 = s1 + 1; if (s2 == NRING) s2 = 0;
             wrow[k][0] = ring_w + s0 * W; wrow[k][1] = ring_w + s1 * W; wrow[k][2] = ring_w + s2 * W;
+            dirty[k] = false;
+            slow[k] = false;
+            if (MODULE == kDrain) {  // tiles that can touch the outlet take the shared-memory path
+                const int c0 = tile.x0 + it_col[k] - 1;
+                slow[k] = p.ds.drainrow >= row0[k] && p.ds.drainrow <= row0[k] + 2 && p.ds.draincol >= c0 && p.ds.draincol <= c0 + 4;
+            }
+            if (run[k] && !slow[k]) {
+                const int jl = it_col[k] - 1;
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+#pragma unroll
+                    for (int cc = 0; cc < 5; cc++) dd[k][r][cc] = wrow[k][r][DOFF + jl + cc];
+#pragma unroll
+                    for (int cc = 0; cc < 3; cc++) wt[k][r][cc] = wrow[k][r][jl + cc];
+                }
+            }
         }
-        constexpr int DOFF = NRING * W;  // ring_d = ring_w + DOFF
 
-#pragma unroll 1
-        for (int cofs = 0; cofs < 3; cofs++) {
-            Tile<T> tl[IPT];
-            bool any = false;
+        auto substep = [&](auto cofs_tag) {
+            constexpr int COFS = decltype(cofs_tag)::value;
 #pragma unroll
             for (int k = 0; k < IPT; k++) {
-                const int j = it_col[k] + cofs;  // centre column inside the window
-                tl[k].active = false;
-                if (run[k]) {
-                    if (MODULE == kDrain) {
-                        const int crow = row0[k] + 1, ccol = tile.x0 + j;
-                        const int orow = p.ds.drainrow - crow, ocol = p.ds.draincol - ccol;
-                        if (orow >= -1 && orow <= 1 && ocol >= -1 && ocol <= 1) {
-                            if (orow != 0 || ocol != 0) {
-                                T evo, evc;
-                                bool drained;
-                                relax_tile_at_outlet<T>(wrow[k][0], wrow[k][1], wrow[k][2], wrow[k][0] + DOFF, wrow[k][1] + DOFF,
-                                                        wrow[k][2] + DOFF, j, orow, ocol, &evo, &evc, &drained);
-                                // only the CTA that owns the centre reports the event (halo copies recompute it)
-                                if (drained && tile.owns_row(crow) && tile.owns_col(ccol)) {
-                                    DrainEvent<T>* ev = p.ds.events + p.launch_parity * kEventsPerBuffer + (it_ph[k] / 3) * 9 + it_q[k] * 3 + cofs;
-                                    ev->w_outlet = evo;
-                                    ev->w_centre = evc;
-                                    ev->valid = 1;
-                                }
+                if (!run[k]) continue;
+                const int j = it_col[k] + COFS;  // centre column inside the window
+                if (MODULE == kDrain && slow[k]) {
+                    const int crow = row0[k] + 1, ccol = tile.x0 + j;
+                    const int orow = p.ds.drainrow - crow, ocol = p.ds.draincol - ccol;
+                    T* w0 = wrow[k][0]; T* w1 = wrow[k][1]; T* w2 = wrow[k][2];
+                    if (orow >= -1 && orow <= 1 && ocol >= -1 && ocol <= 1) {
+                        if (orow != 0 || ocol != 0) {
+                            T evo, evc;
+                            bool drained;
+                            relax_tile_at_outlet<T>(w0, w1, w2, w0 + DOFF, w1 + DOFF, w2 + DOFF, j, orow, ocol, &evo, &evc, &drained);
+                            // only the CTA that owns the centre reports the event (halo copies recompute it)
+                            if (drained && tile.owns_row(crow) && tile.owns_col(ccol)) {
+                                DrainEvent<T>* ev = p.ds.events + p.launch_parity * kEventsPerBuffer + (it_ph[k] / 3) * 9 + it_q[k] * 3 + COFS;
+                                ev->w_outlet = evo;
+                                ev->w_centre = evc;
+                                ev->valid = 1;
                             }
-                            continue;
+                        }
+                    } else {
+                        relax_tile<T, MODULE>(w0, w1, w2, w0 + DOFF, w1 + DOFF, w2 + DOFF, j);
+                    }
+                    continue;
+                }
+                if (COFS > 0) {  // slide: drop the published left column, read the entering right column
+#pragma unroll
+                    for (int r = 0; r < 3; r++) {
+                        wt[k][r][0] = wt[k][r][1];
+                        wt[k][r][1] = wt[k][r][2];
+                        wt[k][r][2] = wrow[k][r][j + 1];
+                    }
+                }
+                const bool active = (wt[k][1][1] > T(0)) && is_valid_elevation(dd[k][1][COFS + 1]);
+                if (active) {
+                    relax_window<T, MODULE, COFS>(wt[k], dd[k]);
+                    dirty[k] = true;
+                }
+                if (dirty[k]) {
+                    if (COFS < 2) {
+#pragma unroll
+                        for (int r = 0; r < 3; r++) wrow[k][r][j - 1] = wt[k][r][0];
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 3; r++) {
+                            wrow[k][r][j - 1] = wt[k][r][0];
+                            wrow[k][r][j] = wt[k][r][1];
+                            wrow[k][r][j + 1] = wt[k][r][2];
                         }
                     }
-                    tile_load(tl[k], wrow[k][0], wrow[k][1], wrow[k][2], wrow[k][0] + DOFF, wrow[k][1] + DOFF, wrow[k][2] + DOFF, j);
-                    any = any || tl[k].active;
                 }
             }
-            if (any) {
-                // inactive tiles of this thread ride along on dead values; they are not stored
-                tiles_relax<T, MODULE, IPT>(tl);
-#pragma unroll
-                for (int k = 0; k < IPT; k++)
-                    if (tl[k].active) tile_store(tl[k], wrow[k][0], wrow[k][1], wrow[k][2], it_col[k] + cofs);
-            }
-            if (cofs == 2) fence_proxy_async();  // make this step's smem writes visible to the bulk-store engine
-            __syncthreads();
-        }
+        };
+        substep(std::integral_constant<int, 0>{});
+        __syncthreads();
+        substep(std::integral_constant<int, 1>{});
+        __syncthreads();
+        substep(std::integral_constant<int, 2>{});
+        fence_proxy_async();  // make this step's smem writes visible to the bulk-store engine
+        __syncthreads();
 
-        if (tid == 0) {
-            // rows finished by the last phase in this step: C-type rows 3m+2 .. 3m+4
-            bool any = false;
-            for (int t = 0; t < NT; t++) {
-                const int m = tile.triple(s, NPH - 1, t);
-                for (int k = 0; k < 3; k++) {
-                    const int row = 3 * m + 2 + k;
-                    if (!tile.owns_row(row)) continue;
-                    const size_t dst = (size_t)(row + kPadTop) * (size_t)p.g.pitch + col0 + CFG::HL;
-                    bulk_store(p.w_out + dst, ring_w + (size_t)tile.ring_slot(row) * W + CFG::HL, CFG::TWV * sizeof(T));
-                    any = true;
-                }
-            }
-            if (any) bulk_commit();
-            // ring slots reused by the next prefetch must have been read out by their stores:
-            // allow only the group committed just now to be in flight
-            bulk_wait_read<1>();
-        }
-        // No extra barrier: the next loads are issued by thread 0 after its wait above, and every
-        // thread's next access to a reloaded slot is behind that load's mbarrier.
     }
-    if (tid == 0) bulk_wait_read<0>();
 }
 
 }  // namespace wdpm

@@ -91,6 +91,12 @@ WDPM_HD void tile_store(const Tile<T>& t, T* w0, T* w1, T* w2, int j) {
 }
 
 // One neighbour step, branch-free. wc is the centre's running water.
+//
+// The reference does  flow = mini(flow, wc); wc -= flow; wn += flow  under `if (h > 0)`.
+// Here the `if` becomes a select of the amount given: when h <= 0 the amount is -0.0, the
+// additive identity that preserves even a negative zero in wn (x + -0.0 == x bit for bit) and
+// leaves wc unchanged (wc is never negative nor -0 for an active centre). The capped case gives
+// wc itself, so wc - wc = +0 exactly as in the reference.
 template <typename T, int MODULE>
 WDPM_HD void push(T dc, T& wc, T dn, T& wn) {
     const T sn = dn + wn;
@@ -102,9 +108,29 @@ WDPM_HD void push(T dc, T& wc, T dn, T& wn) {
     else x = (dc > sn) ? wc : ((dc - dn) + (wc - wn));
     T flow = x * T(0.125);
     if (MODULE == kDrain) flow = (flow <= T(0)) ? T(0) : flow;
-    flow = (flow <= wc) ? flow : wc;
-    wc = pos ? wc - flow : wc;
-    wn = pos ? wn + flow : wn;
+    const bool fits = flow <= wc;
+    const T other = pos ? wc : T(-0.0);   // known before the multiply: off the dependent chain
+    const T give = (pos && fits) ? flow : other;
+    wc = wc - give;
+    wn = wn + give;
+}
+
+// The same eight steps on a register window that slides one column per colour sub-pass:
+// w holds the tile's 3x3 water (rows x cols), d the elevations of the 3x5 cells the tile
+// covers over the three sub-passes; COFS (0,1,2) selects which three elevation columns apply.
+template <typename T, int MODULE, int COFS>
+WDPM_HD void relax_window(T (&w)[3][3], const T (&d)[3][5]) {
+    const T dc = d[1][COFS + 1];
+    T wc = w[1][1];
+    push<T, MODULE>(dc, wc, d[0][COFS + 0], w[0][0]);
+    push<T, MODULE>(dc, wc, d[0][COFS + 1], w[0][1]);
+    push<T, MODULE>(dc, wc, d[0][COFS + 2], w[0][2]);
+    push<T, MODULE>(dc, wc, d[1][COFS + 0], w[1][0]);
+    push<T, MODULE>(dc, wc, d[1][COFS + 2], w[1][2]);
+    push<T, MODULE>(dc, wc, d[2][COFS + 0], w[2][0]);
+    push<T, MODULE>(dc, wc, d[2][COFS + 1], w[2][1]);
+    push<T, MODULE>(dc, wc, d[2][COFS + 2], w[2][2]);
+    w[1][1] = wc;
 }
 
 // The eight neighbour steps of one tile (only meaningful when t.active).

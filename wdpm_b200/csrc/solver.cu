@@ -47,7 +47,7 @@ struct FusedVariant {
 
 template <typename T, int MODULE, typename CFG, int NTHREADS, int MINB>
 cudaError_t launch_fused(const FusedParams<T>& p, int grid, cudaStream_t st) {
-    k_fused<T, MODULE, CFG, NTHREADS, MINB><<<grid, NTHREADS, fused_smem_bytes<CFG, T>(), st>>>(p);
+    k_fused<T, MODULE, CFG, NTHREADS, MINB><<<grid, NTHREADS + 32, fused_smem_bytes<CFG, T>(), st>>>(p);  // +1 data-movement warp
     return cudaGetLastError();
 }
 
@@ -91,7 +91,7 @@ const std::vector<FusedVariant<double>>& fused_variants<double>() {
         make_variant<double, MwCfg<256, 1, 1, 2>, 256, 2>(),   // 5: two CTAs per SM
         make_variant<double, MwCfg<256, 1, 2, 2>, 512, 1>(),   // 6: two iterations per launch
         make_variant<double, MwCfg<512, 1, 1, 2>, 256, 1>(),   // 7: as 1, two tiles per thread
-        make_variant<double, MwCfg<320, 2, 1, 2>, 1024, 1>(),  // 8: two triples per phase, 32 warps
+        make_variant<double, MwCfg<384, 2, 1, 1>, 384, 1>(),   // 8: two triples per phase, two tiles per thread (exact fit)
         make_variant<double, MwCfg<384, 2, 1, 1>, 256, 1>(),   // 9: two triples per phase, three tiles per thread
         make_variant<double, MwCfg<384, 2, 1, 1>, 768, 1>(),   // 10: two triples per phase, 24 warps, one tile per thread
     };
@@ -107,7 +107,7 @@ const std::vector<FusedVariant<float>>& fused_variants<float>() {
         make_variant<float, MwCfg<1024, 1, 1, 2>, 512, 1>(),   // 5: wide window, two tiles per thread
         make_variant<float, MwCfg<512, 1, 2, 2>, 512, 1>(),    // 6: two iterations per launch
         make_variant<float, MwCfg<512, 1, 1, 2>, 512, 2>(),    // 7: as 1, one tile per thread
-        make_variant<float, MwCfg<768, 2, 1, 1>, 1024, 1>(),   // 8: two triples per phase, 32 warps
+        make_variant<float, MwCfg<640, 2, 1, 1>, 640, 1>(),    // 8: two triples per phase, two tiles per thread
         make_variant<float, MwCfg<768, 2, 1, 1>, 512, 1>(),    // 9: two triples per phase, three tiles per thread
         make_variant<float, MwCfg<384, 2, 1, 1>, 768, 2>(),    // 10: two CTAs of 24 warps per SM
     };
