@@ -219,104 +219,166 @@ def run_ours(args):
     import torch.distributed as dist
 
     from wdpm_b200 import ADD, F32, F64, KERNEL_AUTO, Solver, ascgrid, synth
+    from wdpm_b200.stripes import DistributedSolver
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch N>1 with torch.distributed.run (one process per GPU)")
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("launch N>1 with torch.distributed.run (one process per GPU)")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        raise SystemExit("row-stripe multi-GPU path is not implemented in this round's build yet")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     dtype_code, np_dt, torch_dt, esize = (F64, np.float64, torch.float64, 8) if args.dtype == "f64" else (F32, np.float32, torch.float32, 4)
     size = args.size
+    cells = size * size
     dem_dev = synth.fractal_dem(size, size, seed=size, device=f"cuda:{local_rank}", dtype=torch.float64)
     if args.dtype == "f32":
         dem_dev = dem_dev - dem_dev.min()  # fp32 mode: base elevation removed before rounding
-    dem_host = torch.empty((size, size), dtype=torch_dt, pin_memory=True)
-    dem_host.copy_(dem_dev.to(torch_dt))
+
+    common = dict(dtype=dtype_code, zero_threshold=THRES_MM / 1000, kernel=KERNEL_AUTO, fused_variant=args.variant)
+    if world == 1:
+        s = Solver(size, size, NODATA, ADD, device=local_rank, iters_per_launch=args.iters_per_launch, **common)
+        r0, nrows, o0, orows = 0, size, 0, size
+    else:
+        ds = DistributedSolver(size, size, NODATA, ADD, device=local_rank, **common)
+        s = ds.solver
+        st = ds.stripe
+        r0, nrows, o0, orows = st.band_row0, st.band_rows, st.owned_row0, st.owned_rows
+    # this rank's rows (owned + halos) in pinned host memory: what a host application would hand over
+    dem_host = torch.empty((nrows, size), dtype=torch_dt, pin_memory=True)
+    dem_host.copy_(dem_dev[r0:r0 + nrows].to(torch_dt))
     del dem_dev
     torch.cuda.empty_cache()
-    water_host = torch.zeros((size, size), dtype=torch_dt, pin_memory=True)
+    water_host = torch.zeros((nrows, size), dtype=torch_dt, pin_memory=True)
+    owned_host = water_host[o0 - r0:o0 - r0 + orows]  # contiguous view: the owned rows inside the band
 
-    s = Solver(size, size, NODATA, ADD, dtype=dtype_code, zero_threshold=THRES_MM / 1000, device=local_rank,
-               kernel=KERNEL_AUTO, iters_per_launch=args.iters_per_launch, fused_variant=args.variant)
-    s.upload_ptr(dem_host.data_ptr(), None)
+    def upload(with_water: bool):
+        if world == 1:
+            s.upload_ptr(dem_host.data_ptr(), water_host.data_ptr() if with_water else None)
+        else:
+            ds.upload_band_ptr(dem_host.data_ptr(), water_host.data_ptr() if with_water else None)
+
+    def run_block():
+        return s.run_block(args.block_iters) if world == 1 else ds.run_block(args.block_iters)
+
+    stream = torch.cuda.Stream()
+    s.set_stream(stream.cuda_stream)
+    upload(False)
     s.apply_add(ADD_MM / 1000.0, 1.0)
-    info = s.info()
-    cells = size * size
-    launches0 = info["kernel_launches"]
 
     for _ in range(args.warmup):
-        s.run_block(args.block_iters)
+        run_block()
 
-    # state the timed steps start from, for the CPU baseline sample
-    cpu = None
-    if args.cpu_baseline and rank == 0 and world == 1:
+    # state the timed steps start from, for the CPU baseline sample (N=1, rank 0)
+    do_cpu = args.cpu_baseline and rank == 0 and world == 1
+    if do_cpu:
         s.download_water_ptr(water_host.data_ptr())
         n = min(args.sample_size, size)
-        r0 = (size - n) // 2
-        Dw = ascgrid.pad_grid(dem_host.numpy()[r0:r0 + n, r0:r0 + n].astype(np.float64), NODATA)
-        Ww = ascgrid.pad_grid(water_host.numpy()[r0:r0 + n, r0:r0 + n].astype(np.float64), 0.0)
+        c0 = (size - n) // 2
+        Dw = ascgrid.pad_grid(dem_host.numpy()[c0:c0 + n, c0:c0 + n].astype(np.float64), NODATA)
+        Ww = ascgrid.pad_grid(water_host.numpy()[c0:c0 + n, c0:c0 + n].astype(np.float64), 0.0)
         wet = float(np.count_nonzero(Ww > 0)) / (n * n)
 
+    # ---- timed region: K steps, device time on the solver's stream, max over ranks
     sampler = ClockSampler(physical_gpu_index(local_rank)).start()
-    block_ms, iter_ms, klaunch = [], [], 0
-    last = None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iter_ms, klaunch, last = [], 0, None
+    barrier()
+    ev0.record(stream)
     for _ in range(args.steps):
-        r = s.run_block(args.block_iters)
-        block_ms.append(r.block_ms)
+        r = run_block()
         iter_ms.append(r.iterate_ms)
         klaunch += r.launches
         last = r
+    ev1.record(stream)
+    barrier()
     clocks = sampler.stop()
-    total_ms = float(sum(block_ms))
+    total_ms = max_over_ranks(ev0.elapsed_time(ev1))
     value = cells * args.block_iters * args.steps / (total_ms / 1e3)
 
-    # end to end: host buffers in, host buffers out, every step
-    s.download_water_ptr(water_host.data_ptr())
-    t_e2e = []
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(e2e_steps):
-        t = time.perf_counter()
-        s.upload_ptr(dem_host.data_ptr(), water_host.data_ptr())
-        r2 = s.run_block(args.block_iters)
+    # ---- end to end: host buffers in, host buffers out, every step (max over ranks, wall clock
+    # bracketed by barriers since the host<->device copies are synchronous calls)
+    if world == 1:
         s.download_water_ptr(water_host.data_ptr())
-        t_e2e.append(time.perf_counter() - t)
+    else:
+        # refresh the whole band (halos too) so the re-upload resumes the same state
+        s.download_water_ptr(owned_host.data_ptr())
+        parts = [None] * world
+        dist.all_gather_object(parts, (o0, owned_host.numpy()[[0, 1, 2, 3, 4, 5, -3, -2, -1]].copy()))
+        if rank > 0:
+            water_host[0:o0 - r0] = torch.from_numpy(parts[rank - 1][1][-(o0 - r0):])
+        if rank + 1 < world:
+            nb = nrows - (o0 - r0) - orows
+            water_host[o0 - r0 + orows:] = torch.from_numpy(parts[rank + 1][1][:nb])
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        upload(True)
+        r2 = run_block()
+        s.download_water_ptr(owned_host.data_ptr() if world > 1 else water_host.data_ptr())
         klaunch += r2.launches
-    e2e_value = cells * args.block_iters * e2e_steps / sum(t_e2e)
+        if world > 1 and e2e_steps > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, owned_host.numpy()[[0, 1, 2, 3, 4, 5, -3, -2, -1]].copy())
+            if rank > 0:
+                water_host[0:o0 - r0] = torch.from_numpy(parts[rank - 1][-(o0 - r0):])
+            if rank + 1 < world:
+                nb = nrows - (o0 - r0) - orows
+                water_host[o0 - r0 + orows:] = torch.from_numpy(parts[rank + 1][:nb])
+    barrier()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = cells * args.block_iters * e2e_steps / t_e2e
 
     info2 = s.info()
     K = info2["iters_per_launch"]
     iter_launches = args.block_iters // K
+    my_cells = orows * size
     peak, peak_src = measured_peak_gbs()
     launch_ms = float(np.mean(iter_ms)) / iter_launches
-    achieved = cells * 3 * esize * K / (launch_ms / 1e3) / 1e9
+    achieved = my_cells * 3 * esize * K / (launch_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_fused" if info2["kernel"] == 2 else "k_colour",
-                "launch_ms": launch_ms, "algorithmic_bytes_per_launch": cells * 3 * esize * K, "peak_source": peak_src}
+                "traffic": None, "kernel": "k_fused" if info2["kernel"] == 2 else "k_colour", "launch_ms": launch_ms,
+                "algorithmic_bytes_per_launch": my_cells * 3 * esize * K, "peak_source": peak_src, "per": "GPU (slowest rank's launch time)"}
 
     line = {
         "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, world),
-        "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": 2 * cells * esize,
-                "d2h_bytes_per_step": cells * esize + 64, "steps": e2e_steps},
+        "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": 2 * nrows * size * esize * world if world > 1 else 2 * cells * esize,
+                "d2h_bytes_per_step": cells * esize + 64 * world, "steps": e2e_steps},
         "gpu_launches": int(klaunch), "clocks": clocks, "roofline": roofline,
-        "state": {"max_diff": last.max_diff, "wet_fraction": last.wet_cells / cells, "iterations_done": (args.warmup + args.steps + e2e_steps) * args.block_iters},
+        "state": {"max_diff": last.max_diff, "wet_fraction": last.wet_cells / cells,
+                  "iterations_done": (args.warmup + args.steps + e2e_steps) * args.block_iters},
         "tiling": {k: info2[k] for k in ("kernel", "strip_cols", "window_cols", "chunk_rows", "grid_ctas", "cta_threads", "smem_bytes", "iters_per_launch", "sm_count")},
     }
-    if args.cpu_baseline and rank == 0 and world == 1:
+    if do_cpu:
         v, kind, threads, n_it, dt = time_cpu_sample(Dw, Ww, args.cpu_budget)
         line["cpu_baseline"] = {"value": v, "unit": "cell-updates/s", "cores": threads, "kind": kind,
                                 "sample": f"{Dw.shape[0]-2}x{Dw.shape[1]-2} centre window of the same DEM in the state after warm-up "
                                           f"(wet fraction {wet:.3f}), {n_it} iterations in {dt:.1f} s"}
-    s.close()
+    if world == 1:
+        s.close()
+    else:
+        ds.close()
+        dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(line))
 

@@ -70,10 +70,10 @@ typedef struct wdpm_config {
     double zero_threshold; /* metres; "thres" of src/WDPMCL.c:420, applied at :1055-1065 */
     int32_t device;       /* CUDA device ordinal */
     int32_t kernel;       /* WDPM_KERNEL_* */
-    /* Row-stripe partition (multi-GPU). A single-GPU solver sets stripe_row0 = 0,
-     * stripe_rows = rows. Otherwise this solver owns interior rows
-     * [stripe_row0, stripe_row0 + stripe_rows) (0-based, unpadded) of a DEM with
-     * `rows` rows in total; see wdpm_stripe_* below. */
+    /* Row-stripe partition (multi-GPU). A single-GPU solver sets both to 0. Otherwise
+     * this solver owns PADDED rows [stripe_row0, stripe_row0 + stripe_rows) of a DEM
+     * whose padded rows are 0..rows+1; stripe_row0 must be a multiple of 3. See
+     * wdpm_stripe_* below. */
     int32_t stripe_row0;
     int32_t stripe_rows;
     int32_t iters_per_launch; /* fused kernel: iterations carried per HBM round trip (0 = default) */
@@ -105,8 +105,9 @@ int wdpm_create(const wdpm_config *cfg, wdpm_solver **out);
 int wdpm_destroy(wdpm_solver *s);
 
 /* replaces flatten + clCreateBuffer + clEnqueueWriteBuffer (src/WDPMCL.c:1129-1153),
- * done once instead of once per block. `water` may be NULL (all zero). For a
- * stripe solver the arrays hold only the stripe's rows (stripe_rows x cols). */
+ * done once instead of once per block. `water` may be NULL (all zero). Stripe
+ * solvers use wdpm_stripe_upload instead; their download returns the owned interior
+ * rows only (see wdpm_stripe_band). */
 int wdpm_upload(wdpm_solver *s, const void *dem, const void *water);
 /* replaces only the water upload (resume from a scratch file, src/WDPMCL.c:668-673) */
 int wdpm_upload_water(wdpm_solver *s, const void *water);
@@ -168,24 +169,49 @@ int wdpm_fused_variant_info(int32_t variant, int32_t dtype, int32_t *window_cols
                             int32_t *iters_per_launch, int32_t *cta_threads, int32_t *smem_bytes);
 
 /* ---- row-stripe partition across GPUs (one solver per GPU) -----------------
- * Each stripe keeps halo rows of its neighbours' water. After every launch the
- * rows a neighbour needs are pushed into that neighbour's halo over NVLink.
- * Peers are wired either in-process (pointers) or across processes through CUDA
- * IPC handles exchanged by the host (e.g. torch.distributed all_gather). */
+ * New work: the reference is single-device (src/WDPMCL.c:98-118). The padded DEM
+ * (rows 0..rows+1, src/WDPMCL.c:795-807) is cut into contiguous bands of padded
+ * rows, band starts being multiples of 3 so every cell keeps its colour. A stripe
+ * solver is created with cfg.rows/cols = the WHOLE DEM's size, cfg.stripe_row0 =
+ * first padded row it owns and cfg.stripe_rows = number of padded rows it owns
+ * (0 = not a stripe). It also keeps WDPM_STRIPE_HALO_ABOVE rows of the band above
+ * and WDPM_STRIPE_HALO_BELOW rows of the band below: what one fused iteration
+ * needs to produce its owned rows exactly. After every iteration each stripe
+ * writes the rows its neighbours need straight into their memory over NVLink
+ * (peer stores) and raises an arrival flag there; a neighbour's next iteration
+ * waits on that flag on the device. Per-block reductions stay per stripe; the
+ * host combines them (max / sum in stripe order).
+ * Only the fused kernel with one iteration per launch supports stripes. */
+#define WDPM_STRIPE_HALO_ABOVE 3
+#define WDPM_STRIPE_HALO_BELOW 6
 #define WDPM_IPC_HANDLE_BYTES 64
 typedef struct wdpm_stripe_endpoint {
-    uint8_t water_a[WDPM_IPC_HANDLE_BYTES]; /* cudaIpcMemHandle_t of ping buffer */
-    uint8_t water_b[WDPM_IPC_HANDLE_BYTES]; /* cudaIpcMemHandle_t of pong buffer */
-    uint8_t flags[WDPM_IPC_HANDLE_BYTES];   /* cudaIpcMemHandle_t of arrival flags */
+    uint8_t water_a[WDPM_IPC_HANDLE_BYTES]; /* cudaIpcMemHandle_t of the ping water buffer */
+    uint8_t water_b[WDPM_IPC_HANDLE_BYTES]; /* cudaIpcMemHandle_t of the pong water buffer */
+    uint8_t flags[WDPM_IPC_HANDLE_BYTES];   /* cudaIpcMemHandle_t of the arrival flags */
     int32_t device;
     int32_t stripe_row0;
     int32_t stripe_rows;
-    int32_t reserved;
+    int32_t pitch;      /* elements per device row: must match between neighbours */
+    int64_t pid;        /* exporting process, to tell in-process neighbours apart */
+    uint64_t local_ptr; /* the exporting solver's address (valid only inside process `pid`) */
 } wdpm_stripe_endpoint;
 int wdpm_stripe_export(wdpm_solver *s, wdpm_stripe_endpoint *self);
-/* `above` = the stripe holding smaller row numbers, `below` = larger; NULL at the DEM edge. */
+/* `above` = the stripe holding smaller row numbers, `below` = larger; NULL at the DEM edge.
+ * Endpoints from this process are wired by pointer, others through CUDA IPC. */
 int wdpm_stripe_connect(wdpm_solver *s, const wdpm_stripe_endpoint *above,
                         const wdpm_stripe_endpoint *below);
+/* Upload `band_rows` whole rows of the UNPADDED dem / water arrays starting at interior row
+ * `band_row0` (0-based) - the band must cover the stripe's owned rows plus its halos, clipped to
+ * the DEM (wdpm_stripe_band tells which rows those are). water may be NULL. */
+int wdpm_stripe_band(wdpm_solver *s, int32_t *band_row0, int32_t *band_rows, int32_t *owned_row0,
+                     int32_t *owned_rows);
+int wdpm_stripe_upload(wdpm_solver *s, const void *dem_band, const void *water_band,
+                       int32_t band_row0, int32_t band_rows);
+/* One iteration in two halves, for hosts that drive several in-process stripes in lockstep on
+ * one GPU (tests): phase 0 = launch the iteration kernel, phase 1 = push halos to neighbours.
+ * wdpm_iterate / wdpm_run_block do wait + compute + push per iteration on their own. */
+int wdpm_stripe_phase(wdpm_solver *s, int32_t phase);
 
 #ifdef __cplusplus
 }

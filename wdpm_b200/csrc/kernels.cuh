@@ -42,24 +42,20 @@ __global__ void k_fill(T* __restrict__ a, long long n, T v) {
         a[i] = v;
 }
 
-// Mask the freshly uploaded interior of the DEM in place: dem <= nodata -> +inf (relax.cuh).
+// Mask the freshly uploaded DEM in place: dem <= nodata -> +inf (relax.cuh). Runs over the whole
+// device array; margins already hold +inf, which the mask leaves alone.
 template <typename T>
-__global__ void k_mask_dem(T* __restrict__ d, Geom g, T nodata) {
-    const long long n = (long long)g.R * g.C;
-    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(k / g.C), j = (int)(k - (long long)i * g.C);
-        const size_t a = dev_index(g, i + 1, j + 1);
-        d[a] = mask_elevation(d[a], nodata);
-    }
+__global__ void k_mask_dem(T* __restrict__ d, long long n, T nodata) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
+        d[k] = mask_elevation(d[k], nodata);
 }
 
-// Add-module initial condition, valid cells only (src/WDPMCL.c:778-792).
+// Add-module initial condition, valid cells only (src/WDPMCL.c:778-792). Every cell that is not a
+// valid DEM cell holds +inf elevation, so the whole device array (halo rows of a stripe included)
+// can be swept.
 template <typename T>
-__global__ void k_apply_add(T* __restrict__ w, const T* __restrict__ d, Geom g, T depth, T depth_rof) {
-    const long long n = (long long)g.R * g.C;
-    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(k / g.C), j = (int)(k - (long long)i * g.C);
-        const size_t a = dev_index(g, i + 1, j + 1);
+__global__ void k_apply_add(T* __restrict__ w, const T* __restrict__ d, long long n, T depth, T depth_rof) {
+    for (long long a = blockIdx.x * (long long)blockDim.x + threadIdx.x; a < n; a += (long long)gridDim.x * blockDim.x) {
         if (is_valid_elevation(d[a])) {
             T v = w[a];
             if (v > T(0)) v += depth;
@@ -72,11 +68,8 @@ __global__ void k_apply_add(T* __restrict__ w, const T* __restrict__ d, Geom g, 
 // Subtract-module initial condition (src/WDPMCL.c:919-926): max(w - depth, 0) with the
 // host macro's tie rule (a > b ? a : b).
 template <typename T>
-__global__ void k_apply_subtract(T* __restrict__ w, const T* __restrict__ d, Geom g, T depth) {
-    const long long n = (long long)g.R * g.C;
-    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(k / g.C), j = (int)(k - (long long)i * g.C);
-        const size_t a = dev_index(g, i + 1, j + 1);
+__global__ void k_apply_subtract(T* __restrict__ w, const T* __restrict__ d, long long n, T depth) {
+    for (long long a = blockIdx.x * (long long)blockDim.x + threadIdx.x; a < n; a += (long long)gridDim.x * blockDim.x) {
         if (is_valid_elevation(d[a])) {
             const T v = w[a] - depth;
             w[a] = (v > T(0)) ? v : T(0);
@@ -252,6 +245,74 @@ __device__ __forceinline__ void fold_events(DrainState<T> ds, int parity) {
 template <typename T>
 __global__ void k_fold_events(DrainState<T> ds, int parity) {
     if (blockIdx.x == 0 && threadIdx.x == 0) fold_events(ds, parity);
+}
+
+// ---------------------------------------------------------------------------
+// Row-stripe halo exchange over NVLink (peer stores + arrival flags).
+// After iteration `epoch` a stripe copies, from its freshly written water buffer,
+//   its first HB owned rows  -> the stripe above, as that stripe's rows [P_above, P_above+HB)
+//   its last  HA owned rows  -> the stripe below, as that stripe's rows [-HA, 0)
+// (HA = 3, HB = 6: what one fused iteration reads beyond its owned rows), then
+// publishes `epoch` in the neighbours' arrival flags. Whole device rows are copied.
+// ---------------------------------------------------------------------------
+
+constexpr int kHaloAbove = 3;
+constexpr int kHaloBelow = 6;
+
+struct HaloFlags {
+    int from_above;   // epoch of the last halo received from the stripe above
+    int from_below;
+    int push_count;   // blocks of the running push kernel that have finished copying
+    int error;        // set if a wait gave up
+};
+
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void k_halo_push(const int4* __restrict__ src, int4* __restrict__ dst_above, int4* __restrict__ dst_below,
+                            int row_vecs /* int4 per device row */, int P_self, int P_above, HaloFlags* self_flags,
+                            HaloFlags* flags_above, HaloFlags* flags_below, int epoch) {
+    const long long n_up = dst_above ? (long long)kHaloBelow * row_vecs : 0;
+    const long long n_dn = dst_below ? (long long)kHaloAbove * row_vecs : 0;
+    const int4* src_up = src + (long long)(kPadTop + 0) * row_vecs;
+    int4* dst_up = dst_above + (long long)(kPadTop + P_above) * row_vecs;
+    const int4* src_dn = src + (long long)(kPadTop + P_self - kHaloAbove) * row_vecs;
+    int4* dst_dn = dst_below + (long long)(kPadTop - kHaloAbove) * row_vecs;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_up; i += stride) dst_up[i] = src_up[i];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_dn; i += stride) dst_dn[i] = src_dn[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int done = atomicAdd(&self_flags->push_count, 1);
+        if (done == (int)gridDim.x - 1) {
+            self_flags->push_count = 0;
+            __threadfence_system();
+            if (flags_above) st_release_sys(&flags_above->from_below, epoch);
+            if (flags_below) st_release_sys(&flags_below->from_above, epoch);
+        }
+    }
+}
+
+// Hold the stream until both neighbours' halos of iteration `epoch` have landed.
+__global__ void k_halo_wait(HaloFlags* flags, int need_above, int need_below, int epoch) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (long long spins = 0;; spins++) {
+        const bool ok_a = !need_above || ld_acquire_sys(&flags->from_above) >= epoch;
+        const bool ok_b = !need_below || ld_acquire_sys(&flags->from_below) >= epoch;
+        if (ok_a && ok_b) return;
+        if (spins > 40000000ll) {  // ~10 s: a neighbour died; flag the error instead of hanging the GPU
+            flags->error = 1;
+            return;
+        }
+        __nanosleep(200);
+    }
 }
 
 // ---------------------------------------------------------------------------

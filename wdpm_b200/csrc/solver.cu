@@ -1,11 +1,13 @@
 // C ABI of the B200-native WDPM redistribution solver: device state, launch
 // plumbing and the per-block driver. Declarations and the mapping to the
 // reference's call sites are in include/wdpm_b200.h.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unistd.h>
 #include <vector>
 
 #include "../../include/wdpm_b200.h"
@@ -14,6 +16,9 @@
 using namespace wdpm;
 
 namespace {
+
+constexpr int kDefaultVariantF64 = 10;  // 384-column window, two row triples per phase, 24 compute warps
+constexpr int kDefaultVariantF32 = 7;   // 512-column window, two CTAs of 16 compute warps per SM
 
 thread_local std::string g_err;
 
@@ -147,6 +152,19 @@ struct wdpm_solver {
     OutletCand* d_outlet = nullptr;
     int reduce_blocks = 0;
 
+    // row-stripe state (include/wdpm_b200.h "row-stripe partition")
+    bool stripe = false;
+    int G = 0, P = 0;          // first owned padded row of the whole DEM, owned padded rows
+    HaloFlags* flags = nullptr;
+    struct Peer {
+        bool present = false;
+        void* w[2] = {nullptr, nullptr};
+        HaloFlags* flags = nullptr;
+        int P = 0;
+        bool ipc = false;
+    } above, below;
+    int epoch = 0;             // halo pushes done since the last upload
+
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -204,6 +222,24 @@ int colour_iterations(wdpm_solver* s, int n) {
     return WDPM_OK;
 }
 
+// Copy the rows the neighbours need out of the buffer just written and raise their flags.
+int halo_push(wdpm_solver* s) {
+    s->epoch++;
+    if (!s->above.present && !s->below.present) return WDPM_OK;
+    const int row_vecs = (int)((size_t)s->g.pitch * s->esize / 16);
+    k_halo_push<<<32, 256, 0, s->stream>>>(static_cast<const int4*>(s->w[s->cur]),
+                                           s->above.present ? static_cast<int4*>(s->above.w[s->cur]) : nullptr,
+                                           s->below.present ? static_cast<int4*>(s->below.w[s->cur]) : nullptr, row_vecs, s->P,
+                                           s->above.P, s->flags, s->above.present ? s->above.flags : nullptr,
+                                           s->below.present ? s->below.flags : nullptr, s->epoch);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return WDPM_OK;
+}
+
+template <typename T>
+int fused_launch_only(wdpm_solver* s);
+
 template <typename T>
 int fused_iterations(wdpm_solver* s, int n) {
     const FusedVariant<T>& v = fused_variants<T>()[s->variant];
@@ -219,10 +255,18 @@ int fused_iterations(wdpm_solver* s, int n) {
         p.total_triples = s->total_triples;
         p.launch_parity = s->launch_parity;
         p.ds = drain_state<T>(s);
+        if (s->stripe && s->epoch > 0 && (s->above.present || s->below.present)) {
+            k_halo_wait<<<1, 32, 0, s->stream>>>(s->flags, s->above.present, s->below.present, s->epoch);
+            s->launches++;
+        }
         CUDA_TRY(v.launch[s->module](p, s->n_strips * s->n_chunks, s->stream));
         s->launches++;
         s->cur ^= 1;
         s->launch_parity ^= 1;
+        if (s->stripe) {
+            const int rc = halo_push(s);
+            if (rc) return rc;
+        }
     }
     if (s->module == WDPM_DRAIN && n_launch > 0) {
         k_fold_events<T><<<1, 32, 0, s->stream>>>(drain_state<T>(s), s->launch_parity ^ 1);
@@ -231,6 +275,32 @@ int fused_iterations(wdpm_solver* s, int n) {
     }
     // iterations that do not fill a launch run through the colour kernel (same results)
     return colour_iterations<T>(s, n - n_launch * v.K);
+}
+
+// The iteration kernel alone (no halo wait, no push): hosts driving in-process stripes in lockstep.
+template <typename T>
+int fused_launch_only(wdpm_solver* s) {
+    const FusedVariant<T>& v = fused_variants<T>()[s->variant];
+    FusedParams<T> p;
+    p.w_in = static_cast<const T*>(s->w[s->cur]);
+    p.w_out = static_cast<T*>(s->w[s->cur ^ 1]);
+    p.dem = static_cast<const T*>(s->dem);
+    p.g = s->g;
+    p.n_strips = s->n_strips;
+    p.chunk_triples = s->chunk_triples;
+    p.total_triples = s->total_triples;
+    p.launch_parity = s->launch_parity;
+    p.ds = drain_state<T>(s);
+    CUDA_TRY(v.launch[s->module](p, s->n_strips * s->n_chunks, s->stream));
+    s->launches++;
+    s->cur ^= 1;
+    s->launch_parity ^= 1;
+    if (s->module == WDPM_DRAIN) {
+        k_fold_events<T><<<1, 32, 0, s->stream>>>(drain_state<T>(s), s->launch_parity ^ 1);
+        s->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return WDPM_OK;
 }
 
 template <typename T>
@@ -248,6 +318,11 @@ int run_block_t(wdpm_solver* s, int n_iters, wdpm_block_result* out) {
     const long long n = s->g.cells_dev();
     const long long launches0 = s->launches;
     CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
+    if (s->stripe && s->epoch > 0 && (s->above.present || s->below.present)) {
+        // the neighbours' last halo push must land before the threshold pass touches the halo rows
+        k_halo_wait<<<1, 32, 0, s->stream>>>(s->flags, s->above.present, s->below.present, s->epoch);
+        s->launches++;
+    }
     k_block_prologue<T><<<grid_for(n, 256, s->sm_count), 256, 0, s->stream>>>(
         static_cast<T*>(s->w[s->cur]), static_cast<T*>(s->oldw), n, (T)s->cfg.zero_threshold);
     s->launches++;
@@ -373,8 +448,17 @@ int wdpm_create(const wdpm_config* cfg, wdpm_solver** out) {
     if (cfg->dtype != WDPM_F32 && cfg->dtype != WDPM_F64) return fail(WDPM_E_ARG, "dtype must be WDPM_F32 or WDPM_F64");
     if (cfg->module < WDPM_ADD || cfg->module > WDPM_DRAIN) return fail(WDPM_E_ARG, "unknown module");
     if (cfg->kernel < WDPM_KERNEL_AUTO || cfg->kernel > WDPM_KERNEL_FUSED) return fail(WDPM_E_ARG, "unknown kernel selector");
-    if (cfg->stripe_row0 != 0 || (cfg->stripe_rows != 0 && cfg->stripe_rows != cfg->rows))
-        return fail(WDPM_E_UNSUPPORTED, "row-stripe solvers are not implemented in this build");
+    const bool is_stripe = cfg->stripe_rows > 0;
+    if (is_stripe) {
+        if (cfg->stripe_row0 < 0 || cfg->stripe_row0 % 3 != 0) return fail(WDPM_E_ARG, "stripe_row0 must be a non-negative multiple of 3");
+        if (cfg->stripe_row0 + cfg->stripe_rows > cfg->rows + 2) return fail(WDPM_E_ARG, "stripe exceeds the padded DEM");
+        if (cfg->stripe_rows % 3 != 0 && cfg->stripe_row0 + cfg->stripe_rows != cfg->rows + 2)
+            return fail(WDPM_E_ARG, "stripe_rows must be a multiple of 3 unless the stripe ends the DEM");
+        if (cfg->stripe_rows < 9) return fail(WDPM_E_ARG, "a stripe needs at least 9 rows (its neighbours' halos come from it)");
+        if (cfg->kernel == WDPM_KERNEL_COLOUR) return fail(WDPM_E_UNSUPPORTED, "stripes need the fused kernel");
+    } else if (cfg->stripe_row0 != 0) {
+        return fail(WDPM_E_ARG, "stripe_row0 without stripe_rows");
+    }
     if ((long long)(cfg->rows + 64) * (long long)(cfg->cols + 2048) > (1ll << 40)) return fail(WDPM_E_ARG, "grid too large");
 
     int ndev = 0;
@@ -400,11 +484,15 @@ int wdpm_create(const wdpm_config* cfg, wdpm_solver** out) {
     // kernel + variant
     const long long cells = (long long)(cfg->rows + 2) * (cfg->cols + 2);
     s->kernel = cfg->kernel == WDPM_KERNEL_AUTO ? (cells >= (1ll << 20) ? WDPM_KERNEL_FUSED : WDPM_KERNEL_COLOUR) : cfg->kernel;
+    if (is_stripe) s->kernel = WDPM_KERNEL_FUSED;
+    s->stripe = is_stripe;
+    s->G = cfg->stripe_row0;
+    s->P = is_stripe ? cfg->stripe_rows : cfg->rows + 2;
     const int nvar = s->dtype == WDPM_F64 ? (int)fused_variants<double>().size() : (int)fused_variants<float>().size();
     int variant = cfg->fused_variant;
     if (variant < 0 || variant > nvar) { delete s; return fail(WDPM_E_ARG, "fused_variant out of range"); }
     if (variant == 0) {
-        variant = 1;
+        variant = s->dtype == WDPM_F64 ? kDefaultVariantF64 : kDefaultVariantF32;
         if (cfg->iters_per_launch > 1) {
             variant = 0;
             for (int i = 0; i < nvar; i++) {
@@ -430,11 +518,14 @@ int wdpm_create(const wdpm_config* cfg, wdpm_solver** out) {
         if (e != cudaSuccess) { delete s; return fail(WDPM_E_CUDA, std::string("fused kernel setup: ") + cudaGetErrorString(e)); }
     }
 
-    // geometry (the tests' schedule emulator uses the same formulas)
-    s->g.R = cfg->rows;
+    if (is_stripe && K != 1) { delete s; return fail(WDPM_E_UNSUPPORTED, "stripes need a fused variant with one iteration per launch"); }
+
+    // geometry (the tests' schedule emulator uses the same formulas). A stripe is a grid of P padded
+    // rows whose halo rows live in the row margins above and below.
+    s->g.R = s->P - 2;
     s->g.C = cfg->cols;
     s->n_strips = (cfg->cols + 2 + TWV - 1) / TWV;
-    s->total_triples = (cfg->rows + 2 + 2) / 3;
+    s->total_triples = (s->P + 2) / 3;
     s->g.pitch = ((kPadLeft + s->n_strips * TWV + (W - TWV - HL) + 31) / 32) * 32;
     s->g.nrows_dev = kPadTop + 3 * (s->total_triples + 2 * kMaxItersPerLaunch) + 3;
     choose_chunks(s, K, NT, minb, cfg->fused_chunk_rows);
@@ -452,6 +543,7 @@ int wdpm_create(const wdpm_config* cfg, wdpm_solver** out) {
     }
     s->reduce_blocks = s->sm_count * 8;
     const size_t ev_bytes = 2 * kEventsPerBuffer * (s->dtype == WDPM_F64 ? sizeof(DrainEvent<double>) : sizeof(DrainEvent<float>));
+    if ((e = cudaMalloc((void**)&s->flags, sizeof(HaloFlags))) != cudaSuccess) return cleanup(WDPM_E_NOMEM, cudaGetErrorString(e));
     if ((e = cudaMalloc(&s->totaldrain, 8)) != cudaSuccess || (e = cudaMalloc(&s->events, ev_bytes)) != cudaSuccess ||
         (e = cudaMalloc((void**)&s->partials, sizeof(BlockPartial) * s->reduce_blocks)) != cudaSuccess ||
         (e = cudaMalloc((void**)&s->d_result, sizeof(BlockPartial))) != cudaSuccess ||
@@ -469,6 +561,7 @@ int wdpm_create(const wdpm_config* cfg, wdpm_solver** out) {
         (e = cudaMemsetAsync(s->w[1], 0, grid_bytes, s->stream)) != cudaSuccess ||
         (e = cudaMemsetAsync(s->oldw, 0, grid_bytes, s->stream)) != cudaSuccess ||
         (e = cudaMemsetAsync(s->totaldrain, 0, 8, s->stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(s->flags, 0, sizeof(HaloFlags), s->stream)) != cudaSuccess ||
         (e = cudaMemsetAsync(s->events, 0, ev_bytes, s->stream)) != cudaSuccess)
         return cleanup(WDPM_E_CUDA, cudaGetErrorString(e));
     int rc = s->dtype == WDPM_F64 ? fill_dem<double>(s) : fill_dem<float>(s);
@@ -482,6 +575,13 @@ int wdpm_destroy(wdpm_solver* s) {
     if (!s) return WDPM_OK;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    for (auto* peer : {&s->above, &s->below})
+        if (peer->present && peer->ipc) {
+            cudaIpcCloseMemHandle(peer->w[0]);
+            cudaIpcCloseMemHandle(peer->w[1]);
+            cudaIpcCloseMemHandle(peer->flags);
+        }
+    if (s->flags) cudaFree(s->flags);
     void* ptrs[] = {s->dem, s->w[0], s->w[1], s->oldw, s->totaldrain, s->events, s->partials, s->d_result, s->outlet_partials, s->d_outlet};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -511,13 +611,15 @@ int wdpm_synchronize(wdpm_solver* s) {
 
 int wdpm_upload(wdpm_solver* s, const void* dem, const void* water) {
     if (!s || !dem) return fail(WDPM_E_ARG, "null argument");
+    if (s->stripe) return fail(WDPM_E_STATE, "stripe solvers upload with wdpm_stripe_upload");
     CUDA_TRY(cudaSetDevice(s->device));
     int rc = upload_grid(s, s->dem, dem);
     if (rc) return rc;
     {   // store elevations masked: dem <= nodata -> +inf (relax.cuh)
-        const int grid = grid_for((long long)s->g.R * s->g.C, 256, s->sm_count);
-        if (s->dtype == WDPM_F64) k_mask_dem<double><<<grid, 256, 0, s->stream>>>(static_cast<double*>(s->dem), s->g, s->cfg.nodata);
-        else k_mask_dem<float><<<grid, 256, 0, s->stream>>>(static_cast<float*>(s->dem), s->g, (float)s->cfg.nodata);
+        const long long n = s->g.cells_dev();
+        const int grid = grid_for(n, 256, s->sm_count);
+        if (s->dtype == WDPM_F64) k_mask_dem<double><<<grid, 256, 0, s->stream>>>(static_cast<double*>(s->dem), n, s->cfg.nodata);
+        else k_mask_dem<float><<<grid, 256, 0, s->stream>>>(static_cast<float*>(s->dem), n, (float)s->cfg.nodata);
         s->launches++;
         CUDA_TRY(cudaGetLastError());
     }
@@ -527,6 +629,7 @@ int wdpm_upload(wdpm_solver* s, const void* dem, const void* water) {
 
 int wdpm_upload_water(wdpm_solver* s, const void* water) {
     if (!s) return fail(WDPM_E_ARG, "null solver");
+    if (s->stripe) return fail(WDPM_E_STATE, "stripe solvers upload with wdpm_stripe_upload");
     if (!s->have_dem) return fail(WDPM_E_STATE, "upload the DEM first");
     CUDA_TRY(cudaSetDevice(s->device));
     if (water) {
@@ -543,6 +646,14 @@ int wdpm_download_water(wdpm_solver* s, void* water) {
     if (!s || !water) return fail(WDPM_E_ARG, "null argument");
     if (!s->have_dem) return fail(WDPM_E_STATE, "nothing uploaded yet");
     CUDA_TRY(cudaSetDevice(s->device));
+    if (s->stripe) {  // the owned interior rows only
+        const int lo = (s->G > 1 ? s->G : 1), hi = (s->G + s->P < s->cfg.rows + 1 ? s->G + s->P : s->cfg.rows + 1);
+        const char* src = static_cast<const char*>(s->w[s->cur]) + ((size_t)(lo - s->G + kPadTop) * s->g.pitch + (size_t)(1 + kPadLeft)) * s->esize;
+        CUDA_TRY(cudaMemcpy2DAsync(water, (size_t)s->g.C * s->esize, src, (size_t)s->g.pitch * s->esize, (size_t)s->g.C * s->esize,
+                                   (size_t)(hi - lo), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        return WDPM_OK;
+    }
     CUDA_TRY(cudaMemcpy2DAsync(water, (size_t)s->g.C * s->esize, interior_ptr(s, s->w[s->cur]), (size_t)s->g.pitch * s->esize,
                                (size_t)s->g.C * s->esize, (size_t)s->g.R, cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -553,13 +664,13 @@ int wdpm_apply_add(wdpm_solver* s, double depth, double runoff_fraction) {
     if (!s) return fail(WDPM_E_ARG, "null solver");
     if (!s->have_dem) return fail(WDPM_E_STATE, "upload first");
     CUDA_TRY(cudaSetDevice(s->device));
-    const long long n = (long long)s->g.R * s->g.C;
+    const long long n = s->g.cells_dev();
     const int grid = grid_for(n, 256, s->sm_count);
     if (s->dtype == WDPM_F64)
-        k_apply_add<double><<<grid, 256, 0, s->stream>>>(static_cast<double*>(s->w[s->cur]), static_cast<const double*>(s->dem), s->g,
+        k_apply_add<double><<<grid, 256, 0, s->stream>>>(static_cast<double*>(s->w[s->cur]), static_cast<const double*>(s->dem), n,
                                                          depth, depth * runoff_fraction);
     else
-        k_apply_add<float><<<grid, 256, 0, s->stream>>>(static_cast<float*>(s->w[s->cur]), static_cast<const float*>(s->dem), s->g,
+        k_apply_add<float><<<grid, 256, 0, s->stream>>>(static_cast<float*>(s->w[s->cur]), static_cast<const float*>(s->dem), n,
                                                         (float)depth, (float)(depth * runoff_fraction));
     s->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -570,13 +681,13 @@ int wdpm_apply_subtract(wdpm_solver* s, double depth) {
     if (!s) return fail(WDPM_E_ARG, "null solver");
     if (!s->have_dem) return fail(WDPM_E_STATE, "upload first");
     CUDA_TRY(cudaSetDevice(s->device));
-    const long long n = (long long)s->g.R * s->g.C;
+    const long long n = s->g.cells_dev();
     const int grid = grid_for(n, 256, s->sm_count);
     if (s->dtype == WDPM_F64)
         k_apply_subtract<double><<<grid, 256, 0, s->stream>>>(static_cast<double*>(s->w[s->cur]), static_cast<const double*>(s->dem),
-                                                              s->g, depth);
+                                                              n, depth);
     else
-        k_apply_subtract<float><<<grid, 256, 0, s->stream>>>(static_cast<float*>(s->w[s->cur]), static_cast<const float*>(s->dem), s->g,
+        k_apply_subtract<float><<<grid, 256, 0, s->stream>>>(static_cast<float*>(s->w[s->cur]), static_cast<const float*>(s->dem), n,
                                                              (float)depth);
     s->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -600,7 +711,7 @@ int wdpm_find_outlet(wdpm_solver* s, int32_t* drainrow, int32_t* draincol, doubl
     if (c.index < 0) return fail(WDPM_E_STATE, "no cell with elevation > 0: no outlet");
     s->drainrow = (int)(c.index / (s->g.C + 2));
     s->draincol = (int)(c.index % (s->g.C + 2));
-    if (drainrow) *drainrow = s->drainrow;
+    if (drainrow) *drainrow = s->drainrow + s->G;
     if (draincol) *draincol = s->draincol;
     if (min_elevation) *min_elevation = c.elev;
     return WDPM_OK;
@@ -608,8 +719,8 @@ int wdpm_find_outlet(wdpm_solver* s, int32_t* drainrow, int32_t* draincol, doubl
 
 int wdpm_set_outlet(wdpm_solver* s, int32_t drainrow, int32_t draincol) {
     if (!s) return fail(WDPM_E_ARG, "null solver");
-    if (drainrow < 0 || drainrow > s->g.R + 1 || draincol < 0 || draincol > s->g.C + 1) return fail(WDPM_E_ARG, "outlet outside the padded grid");
-    s->drainrow = drainrow;
+    if (drainrow < 0 || drainrow > s->cfg.rows + 1 || draincol < 0 || draincol > s->g.C + 1) return fail(WDPM_E_ARG, "outlet outside the padded grid");
+    s->drainrow = drainrow - s->G;  // kernels work in the stripe's local rows
     s->draincol = draincol;
     return WDPM_OK;
 }
@@ -637,7 +748,8 @@ int wdpm_get_total_drain(wdpm_solver* s, double* value) {
 
 int wdpm_get_cell_water(wdpm_solver* s, int32_t row, int32_t col, double* value) {
     if (!s || !value) return fail(WDPM_E_ARG, "null argument");
-    if (row < 0 || row > s->g.R + 1 || col < 0 || col > s->g.C + 1) return fail(WDPM_E_ARG, "cell outside the padded grid");
+    row -= s->G;
+    if (row < 0 || row > s->g.R + 1 || col < 0 || col > s->g.C + 1) return fail(WDPM_E_ARG, "cell outside this solver's padded rows");
     CUDA_TRY(cudaSetDevice(s->device));
     const size_t off = ((size_t)(row + kPadTop) * s->g.pitch + (size_t)(col + kPadLeft)) * s->esize;
     double v64 = 0;
@@ -695,14 +807,128 @@ int wdpm_get_info(wdpm_solver* s, wdpm_info* info) {
     return WDPM_OK;
 }
 
+int wdpm_stripe_band(wdpm_solver* s, int32_t* band_row0, int32_t* band_rows, int32_t* owned_row0, int32_t* owned_rows) {
+    if (!s) return fail(WDPM_E_ARG, "null solver");
+    if (!s->stripe) return fail(WDPM_E_STATE, "not a stripe solver");
+    const int R = s->cfg.rows;
+    // padded rows -> interior (0-based) rows: interior = padded - 1, clipped to [1, R]
+    const int blo = std::max(s->G - kHaloAbove, 1), bhi = std::min(s->G + s->P + kHaloBelow, R + 1);
+    const int olo = std::max(s->G, 1), ohi = std::min(s->G + s->P, R + 1);
+    if (band_row0) *band_row0 = blo - 1;
+    if (band_rows) *band_rows = bhi - blo;
+    if (owned_row0) *owned_row0 = olo - 1;
+    if (owned_rows) *owned_rows = ohi - olo;
+    return WDPM_OK;
+}
+
+int wdpm_stripe_upload(wdpm_solver* s, const void* dem_band, const void* water_band, int32_t band_row0, int32_t band_rows) {
+    if (!s || !dem_band) return fail(WDPM_E_ARG, "null argument");
+    if (!s->stripe) return fail(WDPM_E_STATE, "not a stripe solver");
+    int32_t b0, bn;
+    wdpm_stripe_band(s, &b0, &bn, nullptr, nullptr);
+    if (band_row0 != b0 || band_rows != bn) return fail(WDPM_E_ARG, "band must be exactly the rows wdpm_stripe_band reports");
+    CUDA_TRY(cudaSetDevice(s->device));
+    const size_t grid_bytes = (size_t)s->g.cells_dev() * s->esize;
+    const int local0 = band_row0 + 1 - s->G;  // local padded row of the band's first row (>= -kHaloAbove)
+    const size_t off = ((size_t)(local0 + kPadTop) * s->g.pitch + (size_t)(1 + kPadLeft)) * s->esize;
+    int rc = s->dtype == WDPM_F64 ? fill_dem<double>(s) : fill_dem<float>(s);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(static_cast<char*>(s->dem) + off, (size_t)s->g.pitch * s->esize, dem_band, (size_t)s->g.C * s->esize,
+                               (size_t)s->g.C * s->esize, (size_t)band_rows, cudaMemcpyHostToDevice, s->stream));
+    {
+        const long long n = s->g.cells_dev();
+        const int grid = grid_for(n, 256, s->sm_count);
+        if (s->dtype == WDPM_F64) k_mask_dem<double><<<grid, 256, 0, s->stream>>>(static_cast<double*>(s->dem), n, s->cfg.nodata);
+        else k_mask_dem<float><<<grid, 256, 0, s->stream>>>(static_cast<float*>(s->dem), n, (float)s->cfg.nodata);
+        s->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaMemsetAsync(s->w[0], 0, grid_bytes, s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->w[1], 0, grid_bytes, s->stream));
+    s->cur = 0;  // neighbours must agree on which buffer is current
+    if (water_band)
+        CUDA_TRY(cudaMemcpy2DAsync(static_cast<char*>(s->w[s->cur]) + off, (size_t)s->g.pitch * s->esize, water_band,
+                                   (size_t)s->g.C * s->esize, (size_t)s->g.C * s->esize, (size_t)band_rows, cudaMemcpyHostToDevice,
+                                   s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->flags, 0, sizeof(HaloFlags), s->stream));
+    s->epoch = 0;
+    s->have_dem = true;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return WDPM_OK;
+}
+
 int wdpm_stripe_export(wdpm_solver* s, wdpm_stripe_endpoint* self) {
-    (void)s; (void)self;
-    return fail(WDPM_E_UNSUPPORTED, "row-stripe solvers are not implemented in this build");
+    if (!s || !self) return fail(WDPM_E_ARG, "null argument");
+    if (!s->stripe) return fail(WDPM_E_STATE, "not a stripe solver");
+    CUDA_TRY(cudaSetDevice(s->device));
+    std::memset(self, 0, sizeof(*self));
+    static_assert(sizeof(cudaIpcMemHandle_t) == WDPM_IPC_HANDLE_BYTES, "IPC handle size");
+    CUDA_TRY(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(self->water_a), s->w[0]));
+    CUDA_TRY(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(self->water_b), s->w[1]));
+    CUDA_TRY(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(self->flags), s->flags));
+    self->device = s->device;
+    self->stripe_row0 = s->G;
+    self->stripe_rows = s->P;
+    self->pitch = s->g.pitch;
+    self->pid = (int64_t)getpid();
+    self->local_ptr = (uint64_t)(uintptr_t)s;
+    return WDPM_OK;
+}
+
+static int connect_side(wdpm_solver* s, wdpm_solver::Peer& peer, const wdpm_stripe_endpoint* ep, bool is_above) {
+    peer = wdpm_solver::Peer();
+    if (!ep) return WDPM_OK;
+    if (ep->pitch != s->g.pitch) return fail(WDPM_E_ARG, "neighbour stripe has a different row pitch (cols / variant mismatch)");
+    if (is_above ? (ep->stripe_row0 + ep->stripe_rows != s->G) : (s->G + s->P != ep->stripe_row0))
+        return fail(WDPM_E_ARG, "neighbour stripe is not adjacent");
+    peer.P = ep->stripe_rows;
+    if (ep->pid == (int64_t)getpid()) {
+        wdpm_solver* o = reinterpret_cast<wdpm_solver*>((uintptr_t)ep->local_ptr);
+        if (o->device != s->device) {
+            int can = 0;
+            CUDA_TRY(cudaDeviceCanAccessPeer(&can, s->device, o->device));
+            if (!can) return fail(WDPM_E_UNSUPPORTED, "no peer access between the stripes' devices");
+            cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(WDPM_E_CUDA, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        peer.w[0] = o->w[0];
+        peer.w[1] = o->w[1];
+        peer.flags = o->flags;
+        peer.ipc = false;
+    } else {
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, ep->water_a, sizeof(h));
+        CUDA_TRY(cudaIpcOpenMemHandle(&peer.w[0], h, cudaIpcMemLazyEnablePeerAccess));
+        std::memcpy(&h, ep->water_b, sizeof(h));
+        CUDA_TRY(cudaIpcOpenMemHandle(&peer.w[1], h, cudaIpcMemLazyEnablePeerAccess));
+        std::memcpy(&h, ep->flags, sizeof(h));
+        void* f = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&f, h, cudaIpcMemLazyEnablePeerAccess));
+        peer.flags = static_cast<HaloFlags*>(f);
+        peer.ipc = true;
+    }
+    peer.present = true;
+    return WDPM_OK;
 }
 
 int wdpm_stripe_connect(wdpm_solver* s, const wdpm_stripe_endpoint* above, const wdpm_stripe_endpoint* below) {
-    (void)s; (void)above; (void)below;
-    return fail(WDPM_E_UNSUPPORTED, "row-stripe solvers are not implemented in this build");
+    if (!s) return fail(WDPM_E_ARG, "null solver");
+    if (!s->stripe) return fail(WDPM_E_STATE, "not a stripe solver");
+    CUDA_TRY(cudaSetDevice(s->device));
+    int rc = connect_side(s, s->above, above, true);
+    if (rc) return rc;
+    return connect_side(s, s->below, below, false);
+}
+
+int wdpm_stripe_phase(wdpm_solver* s, int32_t phase) {
+    if (!s) return fail(WDPM_E_ARG, "null solver");
+    if (!s->stripe) return fail(WDPM_E_STATE, "not a stripe solver");
+    if (!s->have_dem) return fail(WDPM_E_STATE, "upload first");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (phase == 0) return s->dtype == WDPM_F64 ? fused_launch_only<double>(s) : fused_launch_only<float>(s);
+    if (phase == 1) return halo_push(s);
+    return fail(WDPM_E_ARG, "phase must be 0 or 1");
 }
 
 }  // extern "C"

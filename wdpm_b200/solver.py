@@ -104,7 +104,7 @@ class Solver:
 
     def __init__(self, rows: int, cols: int, nodata: float, module: int, dtype: int = F64, zero_threshold: float = 0.0,
                  device: int = 0, kernel: int = KERNEL_AUTO, iters_per_launch: int = 0, fused_variant: int = 0,
-                 fused_chunk_rows: int = 0):
+                 fused_chunk_rows: int = 0, _stripe: tuple | None = None):
         self._lib = load_library()
         self._h = C.c_void_p()
         cfg = _Config()
@@ -112,7 +112,7 @@ class Solver:
         cfg.rows, cfg.cols, cfg.nodata = rows, cols, nodata
         cfg.dtype, cfg.module, cfg.zero_threshold = dtype, module, zero_threshold
         cfg.device, cfg.kernel = device, kernel
-        cfg.stripe_row0, cfg.stripe_rows = 0, rows
+        cfg.stripe_row0, cfg.stripe_rows = _stripe if _stripe else (0, 0)
         cfg.iters_per_launch, cfg.fused_variant, cfg.fused_chunk_rows = iters_per_launch, fused_variant, fused_chunk_rows
         _check(self._lib.wdpm_create(C.byref(cfg), C.byref(self._h)))
         self.rows, self.cols, self.dtype, self.module, self.nodata = rows, cols, dtype, module, nodata
