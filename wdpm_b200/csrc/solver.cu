@@ -142,7 +142,8 @@ struct wdpm_solver {
 
     void* totaldrain = nullptr;  // device scalar (T)
     void* events = nullptr;      // DrainEvent<T>[2][kEventsPerBuffer]
-    int drainrow = -10, draincol = -10;
+    int drainrow = -10, draincol = -10;  // local padded rows (may lie outside a stripe)
+    bool have_outlet = false;
     int launch_parity = 0;
 
     BlockPartial* partials = nullptr;
@@ -711,6 +712,7 @@ int wdpm_find_outlet(wdpm_solver* s, int32_t* drainrow, int32_t* draincol, doubl
     if (c.index < 0) return fail(WDPM_E_STATE, "no cell with elevation > 0: no outlet");
     s->drainrow = (int)(c.index / (s->g.C + 2));
     s->draincol = (int)(c.index % (s->g.C + 2));
+    s->have_outlet = true;
     if (drainrow) *drainrow = s->drainrow + s->G;
     if (draincol) *draincol = s->draincol;
     if (min_elevation) *min_elevation = c.elev;
@@ -721,6 +723,7 @@ int wdpm_set_outlet(wdpm_solver* s, int32_t drainrow, int32_t draincol) {
     if (!s) return fail(WDPM_E_ARG, "null solver");
     if (drainrow < 0 || drainrow > s->cfg.rows + 1 || draincol < 0 || draincol > s->g.C + 1) return fail(WDPM_E_ARG, "outlet outside the padded grid");
     s->drainrow = drainrow - s->G;  // kernels work in the stripe's local rows
+    s->have_outlet = true;
     s->draincol = draincol;
     return WDPM_OK;
 }
@@ -765,7 +768,7 @@ int wdpm_run_block(wdpm_solver* s, int32_t n_iters, wdpm_block_result* out) {
     if (!s) return fail(WDPM_E_ARG, "null solver");
     if (n_iters < 0) return fail(WDPM_E_ARG, "negative iteration count");
     if (!s->have_dem) return fail(WDPM_E_STATE, "upload first");
-    if (s->module == WDPM_DRAIN && s->drainrow < 0) return fail(WDPM_E_STATE, "Drain needs an outlet: call wdpm_find_outlet or wdpm_set_outlet");
+    if (s->module == WDPM_DRAIN && !s->have_outlet) return fail(WDPM_E_STATE, "Drain needs an outlet: call wdpm_find_outlet or wdpm_set_outlet");
     CUDA_TRY(cudaSetDevice(s->device));
     return s->dtype == WDPM_F64 ? run_block_t<double>(s, n_iters, out) : run_block_t<float>(s, n_iters, out);
 }
@@ -774,7 +777,7 @@ int wdpm_iterate(wdpm_solver* s, int32_t n_iters) {
     if (!s) return fail(WDPM_E_ARG, "null solver");
     if (n_iters < 0) return fail(WDPM_E_ARG, "negative iteration count");
     if (!s->have_dem) return fail(WDPM_E_STATE, "upload first");
-    if (s->module == WDPM_DRAIN && s->drainrow < 0) return fail(WDPM_E_STATE, "Drain needs an outlet");
+    if (s->module == WDPM_DRAIN && !s->have_outlet) return fail(WDPM_E_STATE, "Drain needs an outlet");
     CUDA_TRY(cudaSetDevice(s->device));
     return iterate(s, n_iters);
 }
