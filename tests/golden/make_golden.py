@@ -87,6 +87,13 @@ def main():
         gz(d / "add300.asc", HERE / "ref_opencl_add300.asc.gz")
         shutil.copyfile(d / "add300.txt", HERE / "ref_opencl_add300.txt")
 
+    # usage texts and exit codes of the unmodified binary (WDPMCL.c:308-355)
+    exe = str(po.ref_binary())
+    for name, argv in (("usage_all", []), ("usage_add", ["add"]), ("usage_subtract", ["subtract"]), ("usage_drain", ["drain"]),
+                       ("usage_badcount", ["add", "a", "b", "c"])):
+        res = subprocess.run([exe] + argv, capture_output=True, text=True)
+        (HERE / f"{name}.txt").write_text(f"exit={res.returncode}\n" + res.stdout)
+
     # raw-precision crop vectors from the verbatim kernels
     hdr, dem = ascgrid.read_asc(REF / "dem" / "basin5.asc")
     win = dem[180:276, 200:290].copy()  # mixed valid / NODATA window with relief

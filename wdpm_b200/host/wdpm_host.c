@@ -1,0 +1,565 @@
+/*
+ * wdpmcl_b200 - command-line host of the B200-native WDPM redistribution solver.
+ *
+ * Drop-in for the reference executable WDPMCL (/root/reference/src/WDPMCL.c): same
+ * command line and parameter-file grammar (:308-531), same ESRI ASCII reader and
+ * writer (:533-593, :1533-1599), same printed report (:1616-1857), same
+ * 1000-iteration convergence cadence and stop tests (:1054-1377), same exit codes
+ * (42 usage / missing water file, 1 set-up failure, 255 runtime device failure).
+ * What changes is the solver: every block runs on the GPU through the C ABI of
+ * libwdpm_b200 (include/wdpm_b200.h); grids are uploaded once and stay resident,
+ * the water grid comes back only for a scratch file or the final output.
+ *
+ * The two backend selectors of the reference command line ("0 serial / 1 OpenCL",
+ * "0 OpenCL CPU / 1 OpenCL GPU") are still parsed at their positions; whatever
+ * they say, the CUDA solver runs - there is no CPU path - and the report says so.
+ * The update schedule is the OpenCL branch's (runoff.cl arithmetic); see DESIGN.md
+ * for how that differs from the serial branch in the last bits of Drain/Subtract.
+ *
+ * Environment: WDPM_B200_DEVICE (CUDA ordinal, default 0), WDPM_B200_KERNEL
+ * (0 auto, 1 colour, 2 fused).
+ */
+#define _POSIX_C_SOURCE 200809L
+#include <ctype.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <sys/time.h>
+
+#include "wdpm_b200.h"
+
+enum { BLOCK_ITERATIONS = 1000 }; /* IterationNum, WDPMCL.c:597 */
+enum { EXIT_USAGE = 42 };
+
+typedef struct {
+    char module[32];
+    char dem[512], water[512], output[512], scratch[512];
+    double depth_mm;     /* add / subtract */
+    double runoff_frac;  /* add */
+    double eltol_mm;
+    double drain_tol;    /* drain, m3 */
+    int backend, device_kind; /* the reference's "cpu" and "gpu" flags */
+    double thres_mm;
+    int iter_limit;
+} run_args;
+
+typedef struct {
+    char name[6][104];
+    double value[6];
+    int ncols, nrows;
+    double cellsize, nodata;
+} asc_header;
+
+static int is_module(const char *s) { return !strcmp(s, "add") || !strcmp(s, "subtract") || !strcmp(s, "drain"); }
+static void line(const char *s) { printf("%s\n", s); }
+
+/* ---- usage texts (WDPMCL.c:1658-1745) ------------------------------------ */
+
+static void usage_module(const char *module)
+{
+    line("                                          ");
+    line("Program arguments in order of specification");
+    if (!strcmp(module, "add")) line("Add module specified");
+    else if (!strcmp(module, "subtract")) line("Subtract module specified");
+    else if (!strcmp(module, "drain")) line("Drain module specified");
+    line("DEM file name (string) ");
+    line(!strcmp(module, "add") ? "Water file name (string) - Optional, Use NULL to omit" : "Water file name (string)");
+    line("Output file name (string)");
+    line("Scratch file name (string) - Optional, use NULL to omit");
+    if (!strcmp(module, "add")) {
+        line("Depth of water to add (mm) (real)");
+        line("Water runoff fraction (real)");
+        line("Elevation tolerance (mm) (real)");
+    } else if (!strcmp(module, "subtract")) {
+        line("Depth of water to remove (mm) (real)");
+        line("Elevation tolerance (mm) (real)");
+    } else if (!strcmp(module, "drain")) {
+        line("Elevation tolerance (mm) (real)");
+        line("Drain tolerance (m3) (real)");
+    }
+    line("Specify 0 for serial CPU and 1 for opencl ");
+    line("Specify 0 for OpenCL CPU and 1 for opencl GPU ");
+    line("Zero depth threshold (mm) (real)");
+    line("Maximum number of iterations (integer) - Optional, Use 0 to omit ");
+    line("                                          ");
+}
+
+static void usage_all(void)
+{
+    static const char *const add[] = {"Module name: add", "DEM file name (string)",
+        "Water file name (string) - Optional, use --NULL-- to omit", "Output file name (string)",
+        "Scratch file name (string) - Optional, use --NULL-- to omit", "Depth of water to add (mm) (real)",
+        "Water runoff fraction (real)", "Elevation tolerance (mm) (real)", "Specify 0 for serial CPU and 1 for opencl ",
+        "Specify 0 for OpenCL CPU and 1 for opencl GPU ", "Zero depth threshold (mm) (real) ",
+        "Maximum number of iterations (integer) - Optional, Use 0 to omit", "                                          ",
+        "                                          ", NULL};
+    static const char *const sub[] = {"Module name: subtract", "Path and Name of Report file", "DEM file name (string)",
+        "Water file name (string)", "Output file name (string)", "Scratch file name (string) - Optional, use --NULL-- to omit",
+        "Depth of water to remove (mm) (real)", "Elevation tolerance (mm) (real)", "Specify 0 for serial CPU and 1 for opencl ",
+        "Specify 0 for OpenCL CPU and 1 for opencl GPU ", "Zero depth threshold (mm) (real) ",
+        "Maximum number of iterations (integer) - Optional, Use 0 to omit ", "                                          ",
+        "                                          ", NULL};
+    static const char *const drn[] = {"Module name: drain", "Path and Name of Report file", "DEM file name (string)",
+        "Water file name (string) ", "Output file name (string)", "Scratch file name (string) - Optional, use --NULL-- to omit",
+        "Elevation tolerance (mm) (real)", "Drain tolerance (m3) (real)", "Specify 0 for serial CPU and 1 for opencl ",
+        "Specify 0 for OpenCL CPU and 1 for opencl GPU ", "Zero depth threshold (mm) (real) ",
+        "Maximum number of iterations (integer) - Optional, Use 0 to omit", "                                          ", NULL};
+    const char *const *sets[] = {add, sub, drn};
+    for (int k = 0; k < 3; k++)
+        for (const char *const *p = sets[k]; *p; p++) line(*p);
+}
+
+/* ---- banner and parameter echo (WDPMCL.c:1616-1655, :1748-1797) ----------- */
+
+static void banner(const char *module)
+{
+    static const char blank[] = "                                                                   ";
+    line(blank); line(blank);
+    line("Wetland DEM Ponding Model version 2.0");
+    line("Copyright (c) 2010, 2012, 2014, 2020 Kevin Shook, Centre for Hydrology");
+    line("Developed by Oluwaseun Sharomi, Raymond Spiteri and Tonghe Liu");
+    line("Numerical Simulation Laboratory, University of Saskatchewan.\n");
+    line("--------------------------------------------------------------------");
+    line(blank);
+    line("This program is free software: you can redistribute it and/or modify");
+    line("it under the terms of the GNU General Public License as published by");
+    line("the Free Software Foundation, either version 3 of the License, or");
+    line("(at your option) any later version.");
+    line(blank);
+    line("This program is distributed in the hope that it will be useful,");
+    line("but WITHOUT ANY WARRANTY; without even the implied warranty of");
+    line("MERCHANTABILITY or FITNESS FOR A PARTICULAR PURPOSE.  See the");
+    line("GNU General Public License for more details.");
+    line(blank);
+    line("You should have received a copy of the GNU General Public License");
+    line("along with this program.  If not, see <http://www.gnu.org/licenses/>.");
+    line(blank);
+    if (!strcmp(module, "add")) {
+        line("This program adds water to an ArcGIS ASCII file of water runoff");
+        line("and redistributes water over the DEM");
+    } else if (!strcmp(module, "subtract")) {
+        line("This program removes a depth water to an ArcGIS ASCII file of water depths");
+        line("and redistributes water over the DEM");
+    } else if (!strcmp(module, "drain")) {
+        line("This program drains an ArcGIS ASCII file of water runoff");
+        line("from the lowest point in the DEM, which acts as a drain");
+    }
+    line("From the algorithm of Shapiro, M., & Westervelt, J. (1992). ");
+    line("An Algebra for GIS and Image Processing (pp. 1-22).");
+    line(blank); line(blank);
+}
+
+static void echo_args(const run_args *a)
+{
+    printf("%30s\n", "WDPM Parameters");
+    printf("%30s %s\n", "Function used:", a->module);
+    printf("%30s %s\n", "DEM file:", a->dem);
+    printf("%30s %s\n", "Water file:", a->water);
+    printf("%30s %s\n", "Output file:", a->output);
+    printf("%30s %s\n", "Scratch file:", a->scratch);
+    if (!strcmp(a->module, "add")) {
+        printf("%30s %0.4f %s\n", "Water added:", a->depth_mm, "mm");
+        printf("%30s %0.4f\n", "Runoff fraction:", a->runoff_frac);
+    }
+    if (!strcmp(a->module, "subtract")) printf("%30s %0.4f %s\n", "Water subtracted:", a->depth_mm, "mm");
+    printf("%30s %0.4f %s\n", "Elevation tolerance:", a->eltol_mm, "mm");
+    if (!strcmp(a->module, "drain")) printf("%30s %0.4f %s\n", "Drain tolerance:", a->drain_tol, "m3");
+    printf("%30s %0.4f %s\n", "Zero depth threshold:", a->thres_mm, "mm");
+    if (a->iter_limit == 0) printf("%30s\n", "No iteration limitation is set");
+    else printf("%30s %d\n", "Maximum number of iterations:", a->iter_limit);
+    line("               ");
+    /* the reference prints which OpenCL/serial backend the two flags select (:1781-1796);
+     * here both flags select the same thing */
+    printf("%41s\n", "Using CUDA (sm_100a) for Computation");
+    printf("%40s\n", "backend flags accepted and ignored");
+}
+
+/* ---- arguments: positional argv or a whitespace-token parameter file ------- */
+
+static int tokens_from_file(const char *path, char tok[][512], int max)
+{
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    int n = 0;
+    while (n < max && fscanf(f, "%511s", tok[n]) == 1) n++;
+    fclose(f);
+    return n;
+}
+
+/* v[0] = module, v[1..] = its arguments in the reference's order */
+static int fill_args(run_args *a, int n, char v[][512])
+{
+    memset(a, 0, sizeof *a);
+    snprintf(a->module, sizeof a->module, "%s", v[0]);
+    const int need = !strcmp(a->module, "add") ? 12 : 11;
+    if (!is_module(a->module) || n < need) return -1;
+    int k = 1;
+    snprintf(a->dem, sizeof a->dem, "%s", v[k++]);
+    snprintf(a->water, sizeof a->water, "%s", v[k++]);
+    snprintf(a->output, sizeof a->output, "%s", v[k++]);
+    snprintf(a->scratch, sizeof a->scratch, "%s", v[k++]);
+    if (!strcmp(a->module, "add")) {
+        a->depth_mm = atof(v[k++]);
+        a->runoff_frac = atof(v[k++]);
+        a->eltol_mm = atof(v[k++]);
+    } else if (!strcmp(a->module, "subtract")) {
+        a->depth_mm = atof(v[k++]);
+        a->eltol_mm = atof(v[k++]);
+    } else {
+        a->eltol_mm = atof(v[k++]);
+        a->drain_tol = atof(v[k++]);
+    }
+    a->backend = (int)atof(v[k++]);
+    a->device_kind = (int)atof(v[k++]);
+    a->thres_mm = atof(v[k++]);
+    a->iter_limit = (int)atof(v[k++]);
+    return 0;
+}
+
+static int is_null_name(const char *s)
+{
+    return strlen(s) == 4 && toupper((unsigned char)s[0]) == 'N' && toupper((unsigned char)s[1]) == 'U' &&
+           toupper((unsigned char)s[2]) == 'L' && toupper((unsigned char)s[3]) == 'L';
+}
+
+static int file_exists(const char *p) { struct stat st; return stat(p, &st) == 0; }
+
+/* ---- ESRI ASCII grids ------------------------------------------------------ */
+
+static char *slurp(const char *path, size_t *len)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) return NULL;
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    rewind(f);
+    char *buf = malloc((size_t)n + 1);
+    if (!buf || fread(buf, 1, (size_t)n, f) != (size_t)n) { fclose(f); free(buf); return NULL; }
+    fclose(f);
+    buf[n] = 0;
+    if (len) *len = (size_t)n;
+    return buf;
+}
+
+/* six "name value" pairs, positional (WDPMCL.c:542-555); returns a pointer past them */
+static const char *parse_header(const char *p, asc_header *h)
+{
+    for (int i = 0; i < 6; i++) {
+        int used = 0;
+        if (sscanf(p, " %100s%n", h->name[i], &used) != 1) return NULL;
+        p += used;
+        char *end;
+        h->value[i] = strtod(p, &end);
+        if (end == p) return NULL;
+        p = end;
+    }
+    h->ncols = (int)h->value[0];
+    h->nrows = (int)h->value[1];
+    h->cellsize = h->value[4];
+    h->nodata = h->value[5];
+    return p;
+}
+
+/* rows*cols values in row-major order after the header; missing values stay as `fill` */
+static double *read_grid(const char *path, int rows, int cols, double fill, asc_header *hdr_out)
+{
+    char *buf = slurp(path, NULL);
+    if (!buf) return NULL;
+    asc_header h;
+    const char *p = parse_header(buf, &h);
+    if (!p) { free(buf); return NULL; }
+    if (hdr_out) *hdr_out = h;
+    const size_t n = (size_t)rows * (size_t)cols;
+    double *g = malloc(n * sizeof *g);
+    if (!g) { free(buf); return NULL; }
+    size_t k = 0;
+    for (; k < n; k++) {
+        char *end;
+        const double v = strtod(p, &end);
+        if (end == p) break;
+        g[k] = v;
+        p = end;
+    }
+    for (; k < n; k++) g[k] = fill;
+    free(buf);
+    return g;
+}
+
+/* write_gis, WDPMCL.c:1533-1554: "%f " per value, header formats as there */
+static int write_grid(const char *path, const asc_header *h, const double *g)
+{
+    FILE *f = fopen(path, "w");
+    if (!f) return -1;
+    static char iobuf[1 << 20];
+    setvbuf(f, iobuf, _IOFBF, sizeof iobuf);
+    fprintf(f, "%s %d\n", h->name[0], (int)h->value[0]);
+    fprintf(f, "%s %d\n", h->name[1], (int)h->value[1]);
+    fprintf(f, "%s %14.6f\n", h->name[2], h->value[2]);
+    fprintf(f, "%s %14.6f\n", h->name[3], h->value[3]);
+    fprintf(f, "%s %9.6f\n", h->name[4], h->value[4]);
+    fprintf(f, "%s %14.6f\n", h->name[5], h->value[5]);
+    for (int r = 0; r < h->nrows; r++) {
+        const double *row = g + (size_t)r * h->ncols;
+        for (int c = 0; c < h->ncols; c++) fprintf(f, "%f ", row[c]);
+        fputc('\n', f);
+    }
+    return fclose(f);
+}
+
+/* ---- run ------------------------------------------------------------------- */
+
+static double seconds_since(const struct timeval *t0)
+{
+    struct timeval t;
+    gettimeofday(&t, NULL);
+    return (double)(t.tv_usec - t0->tv_usec) / 1000000 + (double)(t.tv_sec - t0->tv_sec);
+}
+
+static void die_solver(const char *what)
+{
+    printf("error: %s with CUDA solver error (%s)\n", what, wdpm_last_error());
+    exit(-1); /* as exitOnFail, WDPMCL.c:225-232 */
+}
+
+/* what the scratch file and the Add output hold: water with NODATA cells marked (WDPMCL.c:1336-1344, :1386-1392) */
+static void mark_nodata(double *w, const double *dem, size_t n, double nodata)
+{
+    for (size_t k = 0; k < n; k++)
+        if (dem[k] <= nodata) w[k] = nodata;
+}
+
+int main(int argc, char **argv)
+{
+    setbuf(stdout, NULL);
+    static char tok[16][512];
+    int ntok = 0;
+    if (argc == 1) {
+        usage_all();
+        return EXIT_USAGE;
+    }
+    if (argc == 2) {
+        if (is_module(argv[1])) {
+            usage_module(argv[1]);
+            return EXIT_USAGE;
+        }
+        ntok = tokens_from_file(argv[1], tok, 16);
+        if (ntok < 1) {
+            perror("Couldn't read the parameter file");
+            return 1;
+        }
+    } else if (argc == 12 || argc == 13) {
+        for (int i = 1; i < argc; i++) snprintf(tok[ntok++], 512, "%s", argv[i]);
+    } else {
+        usage_module(argv[1]);
+        return EXIT_USAGE;
+    }
+
+    banner(tok[0]);
+    run_args a;
+    if (fill_args(&a, ntok, tok) != 0 || (argc > 2 && argc != (!strcmp(tok[0], "add") ? 13 : 12))) {
+        usage_module(tok[0]);
+        return EXIT_USAGE;
+    }
+    echo_args(&a);
+    const int is_add = !strcmp(a.module, "add"), is_sub = !strcmp(a.module, "subtract"), is_drain = !strcmp(a.module, "drain");
+    /* mm -> m (WDPMCL.c:417-420, :473-476, :528-530) */
+    const double eltol = a.eltol_mm / 1000.0;
+    const double depth = is_add ? a.depth_mm / 1000.0 : a.depth_mm / 1000;
+    const double thres = a.thres_mm / 1000;
+
+    /* DEM header and data */
+    char *hb = slurp(a.dem, NULL);
+    asc_header hdr;
+    if (!hb || !parse_header(hb, &hdr)) {
+        perror("Couldn't read the DEM file");
+        return 1;
+    }
+    free(hb);
+    line("                  ");
+    printf("%30s\n", "ArcGIS file header");
+    printf("%30s %d\n", hdr.name[0], hdr.ncols);
+    printf("%30s %d\n", hdr.name[1], hdr.nrows);
+    for (int i = 2; i < 6; i++) printf("%30s %9.1f\n", hdr.name[i], hdr.value[i]);
+    const int rows = hdr.nrows, cols = hdr.ncols;
+    const size_t n = (size_t)rows * (size_t)cols;
+    const double nodata = hdr.nodata, cellarea = hdr.cellsize * hdr.cellsize;
+    printf("%30s\n", "Setting array sizes");
+    double *dem = read_grid(a.dem, rows, cols, 0.0, NULL);
+    if (!dem) {
+        perror("Couldn't read the DEM file");
+        return 1;
+    }
+    line("           ");
+    line("           ");
+
+    long basincount = 0;
+    for (size_t k = 0; k < n; k++) basincount += dem[k] > nodata;
+
+    /* water: scratch file (resume) > water file > zeros; the messages follow WDPMCL.c:666-989 */
+    double *water = NULL;
+    int resumed = 0;
+    double initial_vol = 0.0;
+    if (!is_null_name(a.scratch)) {
+        if (file_exists(a.scratch)) {
+            line("           ");
+            printf("%30s\n", "Scratch file found");
+            water = read_grid(a.scratch, rows, cols, 0.0, NULL);
+            resumed = 1;
+        } else {
+            line("           ");
+            printf("%30s\n", "No Scratch file found");
+            line("           ");
+            printf("%30s\n", is_sub ? "New Scratch will be saved." : "New Scratch will be saved");
+            line("           ");
+            printf("%30s\n", "Now proceeding with Waterfile checking");
+            line("           ");
+        }
+    }
+    if (!water) {
+        const int named = is_drain || !is_null_name(a.water);
+        if (named && file_exists(a.water)) {
+            printf("%30s\n", "Existing water file found");
+            water = read_grid(a.water, rows, cols, 0.0, NULL);
+            if (!is_drain && !is_null_name(a.scratch)) { /* only this path recomputes the initial volume (:690-699, :846-855) */
+                for (size_t k = 0; k < n; k++)
+                    if (is_add ? dem[k] > nodata : dem[k] > 0) initial_vol += water[k];
+                initial_vol *= cellarea;
+            }
+        } else if (is_drain) {
+            printf("%30s\n", "Error water file missing");
+            return EXIT_USAGE;
+        } else {
+            printf("%30s\n", named ? "Water file missing, will be created" : "Water file will be created");
+            water = calloc(n, sizeof *water);
+        }
+    }
+    if (!water) {
+        perror("Couldn't read the water file");
+        return 1;
+    }
+    if (is_drain) {
+        initial_vol = 0.0;
+        for (size_t k = 0; k < n; k++)
+            if (dem[k] > nodata) initial_vol += water[k];
+        initial_vol *= cellarea;
+    }
+
+    /* solver */
+    wdpm_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.struct_size = sizeof cfg;
+    cfg.rows = rows;
+    cfg.cols = cols;
+    cfg.nodata = nodata;
+    cfg.dtype = WDPM_F64;
+    cfg.module = is_add ? WDPM_ADD : is_sub ? WDPM_SUBTRACT : WDPM_DRAIN;
+    cfg.zero_threshold = thres;
+    cfg.device = getenv("WDPM_B200_DEVICE") ? atoi(getenv("WDPM_B200_DEVICE")) : 0;
+    cfg.kernel = getenv("WDPM_B200_KERNEL") ? atoi(getenv("WDPM_B200_KERNEL")) : WDPM_KERNEL_AUTO;
+    wdpm_solver *sv = NULL;
+    if (wdpm_create(&cfg, &sv) != WDPM_OK) {
+        fprintf(stderr, "Couldn't create the CUDA solver: %s\n", wdpm_last_error());
+        return 1;
+    }
+    if (wdpm_upload(sv, dem, water) != WDPM_OK) die_solver("upload grids");
+    if (!resumed) {
+        if (is_add && wdpm_apply_add(sv, depth, a.runoff_frac) != WDPM_OK) die_solver("add water");
+        if (is_sub && wdpm_apply_subtract(sv, depth) != WDPM_OK) die_solver("subtract water");
+    }
+
+    double total_drain = 0.0;
+    if (is_drain) {
+        int32_t drow = 0, dcol = 0;
+        double minel = 0.0, w_out = 0.0;
+        if (wdpm_find_outlet(sv, &drow, &dcol, &minel) != WDPM_OK) die_solver("locate the drain");
+        if (wdpm_get_cell_water(sv, drow, dcol, &w_out) != WDPM_OK) die_solver("read the drain cell");
+        total_drain = w_out > 0 ? w_out : 0; /* WDPMCL.c:1029 */
+        if (wdpm_set_total_drain(sv, total_drain) != WDPM_OK) die_solver("set totaldrain");
+        line("               ");
+        printf("%30s\n", "Basin summary");
+        printf("%20s %10.4f %s\n", "Basin area:", (double)basincount * cellarea, "m2");
+        printf("%20s %10.4f %s\n", "Initial volume:", initial_vol, "m3");
+        printf("%20s %d\n", "Drain column:", dcol);
+        printf("%20s %d\n", "Drain row:", drow);
+        printf("%20s %10.4f %s\n", "Min DEM elevation:", minel, "m");
+    }
+    line("               ");
+    printf("%30s\n", "Doing calculations");
+    if (is_drain) {
+        printf("%15s %15s %15s %15s %15s\n", "iterations", "max diff", "vol change", "water left", "run time");
+        printf("%13s %14s %15s %16s %17s\n", " ", "(m)", "(m3)", "(m3)", "(s)");
+    } else {
+        printf("%15s %15s %15s\n", "iterations", "max diff", "run time");
+        printf("%13s %14s %15s\n", " ", "(m)", "(s)");
+    }
+
+    /* blocks of 1000 iterations until a stop test fires (WDPMCL.c:1054-1377) */
+    struct timeval t0;
+    gettimeofday(&t0, NULL);
+    int k = 0, done = 0;
+    while (!done) {
+        const double old_drain = total_drain;
+        wdpm_block_result r;
+        if (wdpm_run_block(sv, BLOCK_ITERATIONS, &r) != WDPM_OK) die_solver("run block");
+        k += BLOCK_ITERATIONS;
+        total_drain = r.total_drain;
+        double diffdrain = 0.0;
+        if (is_drain) {
+            diffdrain = fabs(total_drain - old_drain) * cellarea;
+            printf("%7s %d %7s %8.3f %5s %10.1f %5s %12.1f %5s %8.2f\n", "", k, "", r.max_diff, "", diffdrain, "",
+                   r.masked_sum * cellarea, "", seconds_since(&t0));
+        } else {
+            printf("%7s %d %7s %8.3f %5s %8.2f\n", "", k, "", r.max_diff, "", seconds_since(&t0));
+        }
+        done = r.max_diff <= eltol || (is_drain && diffdrain < a.drain_tol) || (a.iter_limit > 0 && k >= a.iter_limit);
+        if (!done && !is_null_name(a.scratch)) {
+            if (wdpm_download_water(sv, water) != WDPM_OK) die_solver("read water for the scratch file");
+            if (is_add) mark_nodata(water, dem, n, nodata);
+            write_grid(a.scratch, &hdr, water);
+        }
+    }
+
+    /* final grid and statistics (WDPMCL.c:1379-1467) */
+    if (wdpm_download_water(sv, water) != WDPM_OK) die_solver("read water");
+    mark_nodata(water, dem, n, nodata);
+    long watercount = 0;
+    double watertotal = 0.0;
+    for (size_t i = 0; i < n; i++) {
+        if (dem[i] > nodata) {
+            watertotal += water[i];
+            if (water[i] > 0.001) watercount++;
+        }
+    }
+    const double final_vol = watertotal * cellarea;
+    const double meanwater = watertotal / ((float)watercount);
+    const double waterfrac = (float)watercount / (float)basincount;
+    const double drainvol = total_drain * cellarea;
+    const double draindepth = (drainvol / ((float)basincount * cellarea)) * 1000;
+    double maxdepth = water[0];
+    for (size_t i = 0; i < n; i++)
+        if (water[i] > maxdepth) maxdepth = water[i];
+    maxdepth *= 1000;
+
+    line("                     ");
+    printf("%30s\n", "WDPM run summary");
+    printf("%20s %10.2f %s\n", "Initial volume", initial_vol, "m3");
+    printf("%20s %10.2f %s\n", "Final volume", final_vol, "m3");
+    printf("%20s %10.2f %s\n", "Volume change", is_drain ? initial_vol - final_vol : final_vol - initial_vol, "m3");
+    if (is_drain) printf("%20s %10.2f %s\n", "Volume drained", drainvol, "m3");
+    printf("%20s %10.4f %s\n", "Final water coverage", waterfrac, "");
+    printf("%20s %10.2f %s\n", "Mean water depth", meanwater * 1000., "mm");
+    if (is_drain) printf("%20s %10.2f %s\n", "Depth drained", draindepth, "mm ");
+    printf("%20s %10.2f %s\n", "Max water depth", maxdepth, "mm ");
+
+    if (write_grid(a.output, &hdr, water) != 0) {
+        perror("Couldn't write the output file");
+        return 1;
+    }
+    printf("%20s %10.2f %s\n", "Run Time", seconds_since(&t0), "s");
+    wdpm_destroy(sv);
+    free(dem);
+    free(water);
+    return 0;
+}
