@@ -354,8 +354,15 @@ def run_ours(args):
     peak, peak_src = measured_peak_gbs()
     launch_ms = float(np.mean(iter_ms)) / iter_launches
     achieved = my_cells * 3 * esize * K / (launch_ms / 1e3) / 1e9
+    kernel_name = "k_fused" if info2["kernel"] == 2 else "k_colour"
+    traffic = None
+    try:  # DRAM bytes per launch from the committed ncu capture of this very configuration, if there is one
+        tj = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
+        traffic = tj[f"{kernel_name}:{args.dtype}:{size}x{size}:{world}gpu"]["traffic_bytes"]
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_fused" if info2["kernel"] == 2 else "k_colour", "launch_ms": launch_ms,
+                "traffic": traffic, "kernel": kernel_name, "launch_ms": launch_ms,
                 "algorithmic_bytes_per_launch": my_cells * 3 * esize * K, "peak_source": peak_src, "per": "GPU (slowest rank's launch time)"}
 
     line = {

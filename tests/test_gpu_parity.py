@@ -191,7 +191,7 @@ def test_basin5_fused_kernel_equals_colour_kernel(cuda_lib, basin5):
     from wdpm_b200 import F64, KERNEL_COLOUR, KERNEL_FUSED, Solver
     hdr, dem = basin5
     res = []
-    for kernel, variant in ((KERNEL_COLOUR, 0), (KERNEL_FUSED, 1), (KERNEL_FUSED, 5), (KERNEL_FUSED, 6)):
+    for kernel, variant in ((KERNEL_COLOUR, 0), (KERNEL_FUSED, 1), (KERNEL_FUSED, 5), (KERNEL_FUSED, 6), (KERNEL_FUSED, 0)):
         s = Solver(hdr.nrows, hdr.ncols, hdr.nodata, 0, dtype=F64, zero_threshold=5e-6, kernel=kernel, fused_variant=variant)
         s.upload(dem, None)
         s.apply_add(0.3, 1.0)
@@ -239,3 +239,19 @@ def test_large_grid_properties(cuda_lib, dt, size):
     pyoracle.Oracle().iterate(W, D, NODATA, 0, n_it)
     m = 18 * n_it + 4
     assert np.array_equal(W[1 + m:-1 - m, 1 + m:-1 - m], outs[1][r0 + m:r0 + n - m, c0 + m:c0 + n - m])
+
+
+def test_basin5_add_300mm_to_convergence(cuda_lib, basin5, tmp_path):
+    """BASELINE.json configs[0]: basin5 Add 300 mm, rof 1.0, tol 1 mm, threshold 0.005 mm. The reference needs
+    320 000 iterations (352 s on 8 host threads through its OpenCL branch, 996 s serial); the output file
+    must equal its file byte for byte (tests/golden/ref_opencl_add300.asc.gz, md5 equal to the serial run's)."""
+    from wdpm_b200.wdpmcl import ModuleParams, default_backend, run_module
+    hdr, dem = basin5
+    rep = run_module(dem, hdr.nodata, hdr.cellsize, ModuleParams("add", depth_mm=300, runoff_fraction=1.0, elevation_tol_mm=1.0,
+                                                                   zero_threshold_mm=0.005), backend=default_backend())
+    assert rep.iterations == 320000
+    path = tmp_path / "add300.asc"
+    ascgrid.write_asc(path, hdr, rep.water)
+    assert path.read_text() == golden_text("ref_opencl_add300.asc.gz")
+    assert "%10.2f" % rep.final_vol == "3301066.70" and "%10.4f" % rep.water_frac == "    0.3062"
+    print(f"cfg1 on GPU: {rep.solver_ms/1e3:.2f} s of device time, {rep.launches} launches")

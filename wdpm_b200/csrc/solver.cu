@@ -19,6 +19,13 @@ namespace {
 
 constexpr int kDefaultVariantF64 = 10;  // 384-column window, two row triples per phase, 24 compute warps
 constexpr int kDefaultVariantF32 = 7;   // 512-column window, two CTAs of 16 compute warps per SM
+// Grids of a few hundred thousand cells (the reference's basin5 is 482 x 471) cannot fill 148 SMs
+// with long chunks: narrow windows, two CTAs per SM and chunks of a few row triples spread the
+// rows over the whole chip in one wave (measured on basin5: 18 us per iteration against 37 us for
+// nine colour launches).
+constexpr int kSmallGridVariantF64 = 5;
+constexpr int kSmallGridVariantF32 = 7;
+constexpr long long kSmallGridCells = 1ll << 22;
 
 thread_local std::string g_err;
 
@@ -388,7 +395,7 @@ void choose_chunks(wdpm_solver* s, int K, int NT, int minb, int forced_rows) {
     const int fill = 3 * K + (3 * K - 1) * (NT + 1);
     double best_cost = 1e300;
     int best_ct = total;
-    const int max_chunks = total / 16 > 0 ? total / 16 : 1;
+    const int max_chunks = total / 3 > 0 ? total / 3 : 1;  // at least three row triples per CTA
     for (int nch = 1; nch <= max_chunks && nch <= 4096; nch++) {
         const int ct = (total + nch - 1) / nch;
         const int real_nch = (total + ct - 1) / ct;
@@ -484,7 +491,7 @@ int wdpm_create(const wdpm_config* cfg, wdpm_solver** out) {
 
     // kernel + variant
     const long long cells = (long long)(cfg->rows + 2) * (cfg->cols + 2);
-    s->kernel = cfg->kernel == WDPM_KERNEL_AUTO ? (cells >= (1ll << 20) ? WDPM_KERNEL_FUSED : WDPM_KERNEL_COLOUR) : cfg->kernel;
+    s->kernel = cfg->kernel == WDPM_KERNEL_AUTO ? WDPM_KERNEL_FUSED : cfg->kernel;
     if (is_stripe) s->kernel = WDPM_KERNEL_FUSED;
     s->stripe = is_stripe;
     s->G = cfg->stripe_row0;
@@ -494,6 +501,7 @@ int wdpm_create(const wdpm_config* cfg, wdpm_solver** out) {
     if (variant < 0 || variant > nvar) { delete s; return fail(WDPM_E_ARG, "fused_variant out of range"); }
     if (variant == 0) {
         variant = s->dtype == WDPM_F64 ? kDefaultVariantF64 : kDefaultVariantF32;
+        if (cells < kSmallGridCells && !is_stripe) variant = s->dtype == WDPM_F64 ? kSmallGridVariantF64 : kSmallGridVariantF32;
         if (cfg->iters_per_launch > 1) {
             variant = 0;
             for (int i = 0; i < nvar; i++) {
