@@ -507,16 +507,16 @@ k_fused(const FusedParams<T> p) {
     // Static work assignment: in every sub-step thread `tid` relaxes tiles number tid,
     // tid+NTHREADS, ... of the NPH*NT*NC tiles (phase-major, then triple slot, then column), so its
     // phase / triple slot / column never change and are decoded once.
-    constexpr int NC = CFG::NC;
-    constexpr int NITEMS = NPH * NT * NC;
+    constexpr int NC = CFG::NC, NCP = CFG::NCP;
+    constexpr int NITEMS = NPH * NT * NCP;
     constexpr int IPT = (NITEMS + NTHREADS - 1) / NTHREADS;
     int it_col[IPT], it_q[IPT], it_ph[IPT], it_mrel[IPT];
     bool it_ok[IPT];
 #pragma unroll
     for (int k = 0; k < IPT; k++) {
         const int item = tid + k * NTHREADS;
-        it_ok[k] = item < NITEMS;
-        const int c = item % NC, pt = item / NC, t = pt % NT, ph = pt / NT;
+        const int c = item % NCP, pt = item / NCP, t = pt % NT, ph = pt / NT;
+        it_ok[k] = item < NITEMS && c < NC;
         it_col[k] = 3 * c + 1;
         it_ph[k] = ph;
         it_q[k] = ph % 3;

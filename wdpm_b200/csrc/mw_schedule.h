@@ -51,6 +51,10 @@ struct MwCfg {
     // tiles per row triple, the same for every tile-start column offset cofs = oj-1 in {0,1,2}:
     // tile c starts at window column 3c+cofs and must end inside the window for cofs = 2.
     static constexpr int NC = (W - 5) / 3 + 1;
+    // Tiles are numbered row-group major; NCP is the numbering stride of a row group. Rounding it up
+    // to a whole number of warps keeps every warp inside one row triple (stride-3 shared-memory
+    // access is then conflict-free); it is done only when it idles fewer than 1 lane in 20.
+    static constexpr int NCP = ((((NC + 31) / 32) * 32 - NC) * 20 < NC) ? ((NC + 31) / 32) * 32 : NC;
     // the oj=1 tessellation covers window columns [0, 3*NC): that is the width the halos eat into
     static constexpr int TWV = ((3 * NC - HL - HR_NEED) / 12) * 12;  // owned columns per strip
     static constexpr int TOP_TRIPLES = K;      // triples staged above the owned rows
