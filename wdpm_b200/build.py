@@ -59,7 +59,7 @@ def build_host(force: bool = False) -> Path | None:
     if not src.exists():
         return None
     if force or _stale(HOST_BIN, [src, ROOT / "include" / "wdpm_b200.h", LIB]):
-        cmd = ["/usr/bin/gcc", "-O2", "-std=c11", "-Wall", "-Wextra", "-I", str(ROOT / "include"), str(src), "-o", str(HOST_BIN),
+        cmd = ["/usr/bin/gcc", "-O2", "-std=c11", "-fopenmp", "-Wall", "-Wextra", "-I", str(ROOT / "include"), str(src), "-o", str(HOST_BIN),
                "-L", str(PKG), "-lwdpm_b200", "-Wl,-rpath,$ORIGIN/..", "-lm"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:

@@ -28,6 +28,10 @@
 #include <sys/stat.h>
 #include <sys/time.h>
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
 #include "wdpm_b200.h"
 
 enum { BLOCK_ITERATIONS = 1000 }; /* IterationNum, WDPMCL.c:597 */
@@ -262,10 +266,55 @@ static const char *parse_header(const char *p, asc_header *h)
     return p;
 }
 
+/* Parallel text -> double. The data section is cut into one byte range per thread; a token belongs
+ * to the range its first character lies in. Pass 1 counts tokens per range, a prefix sum gives each
+ * range its output offset, pass 2 converts with strtod - the conversion fscanf("%lf") itself uses
+ * (WDPMCL.c:1569-1574, :1592-1597), so every value is bit-identical to the reference's reader. */
+static int is_space(char c) { return c == ' ' || c == '\n' || c == '\t' || c == '\r' || c == '\f' || c == '\v'; }
+
+static size_t parse_values(const char *p, const char *end, double *g, size_t n)
+{
+    int nt = 1;
+#ifdef _OPENMP
+    nt = omp_get_max_threads();
+#endif
+    const size_t len = (size_t)(end - p);
+    if (len < (size_t)1 << 16) nt = 1;
+    size_t *count = calloc((size_t)nt + 1, sizeof *count);
+    if (!count) return 0;
+#pragma omp parallel num_threads(nt)
+    {
+        int t = 0;
+#ifdef _OPENMP
+        t = omp_get_thread_num();
+#endif
+        const char *lo = p + len * (size_t)t / (size_t)nt, *hi = p + len * (size_t)(t + 1) / (size_t)nt;
+        size_t c = 0;
+        for (const char *q = lo; q < hi; q++)
+            if (!is_space(*q) && (q == p || is_space(q[-1]))) c++;
+        count[t + 1] = c;
+#pragma omp barrier
+#pragma omp single
+        for (int i = 0; i < nt; i++) count[i + 1] += count[i];
+        size_t k = count[t];
+        for (const char *q = lo; q < hi && k < n; q++) {
+            if (!is_space(*q) && (q == p || is_space(q[-1]))) {
+                char *stop;
+                g[k++] = strtod(q, &stop);
+                if (stop > q) q = stop - 1;
+            }
+        }
+    }
+    const size_t total = count[nt];
+    free(count);
+    return total < n ? total : n;
+}
+
 /* rows*cols values in row-major order after the header; missing values stay as `fill` */
 static double *read_grid(const char *path, int rows, int cols, double fill, asc_header *hdr_out)
 {
-    char *buf = slurp(path, NULL);
+    size_t len = 0;
+    char *buf = slurp(path, &len);
     if (!buf) return NULL;
     asc_header h;
     const char *p = parse_header(buf, &h);
@@ -274,38 +323,69 @@ static double *read_grid(const char *path, int rows, int cols, double fill, asc_
     const size_t n = (size_t)rows * (size_t)cols;
     double *g = malloc(n * sizeof *g);
     if (!g) { free(buf); return NULL; }
-    size_t k = 0;
-    for (; k < n; k++) {
-        char *end;
-        const double v = strtod(p, &end);
-        if (end == p) break;
-        g[k] = v;
-        p = end;
-    }
+    size_t k = parse_values(p, buf + len, g, n);
     for (; k < n; k++) g[k] = fill;
     free(buf);
     return g;
 }
 
-/* write_gis, WDPMCL.c:1533-1554: "%f " per value, header formats as there */
+/* write_gis, WDPMCL.c:1533-1554: "%f " per value, header formats as there. Rows are formatted in
+ * parallel into per-thread buffers (the same printf conversion, so the bytes are the reference's)
+ * and written out in order. */
 static int write_grid(const char *path, const asc_header *h, const double *g)
 {
     FILE *f = fopen(path, "w");
     if (!f) return -1;
-    static char iobuf[1 << 20];
-    setvbuf(f, iobuf, _IOFBF, sizeof iobuf);
     fprintf(f, "%s %d\n", h->name[0], (int)h->value[0]);
     fprintf(f, "%s %d\n", h->name[1], (int)h->value[1]);
     fprintf(f, "%s %14.6f\n", h->name[2], h->value[2]);
     fprintf(f, "%s %14.6f\n", h->name[3], h->value[3]);
     fprintf(f, "%s %9.6f\n", h->name[4], h->value[4]);
     fprintf(f, "%s %14.6f\n", h->name[5], h->value[5]);
-    for (int r = 0; r < h->nrows; r++) {
-        const double *row = g + (size_t)r * h->ncols;
-        for (int c = 0; c < h->ncols; c++) fprintf(f, "%f ", row[c]);
-        fputc('\n', f);
+    int nt = 1;
+#ifdef _OPENMP
+    nt = omp_get_max_threads();
+#endif
+    if (h->nrows < nt) nt = h->nrows > 0 ? h->nrows : 1;
+    char **bufs = calloc((size_t)nt, sizeof *bufs);
+    size_t *used = calloc((size_t)nt, sizeof *used);
+    int failed = !bufs || !used;
+#pragma omp parallel num_threads(nt) if (!failed)
+    {
+        int t = 0;
+#ifdef _OPENMP
+        t = omp_get_thread_num();
+#endif
+        const int r0 = (int)((long long)h->nrows * t / nt), r1 = (int)((long long)h->nrows * (t + 1) / nt);
+        size_t cap = (size_t)(r1 - r0) * ((size_t)h->ncols * 12 + 2) + 512, u = 0;
+        char *b = malloc(cap);
+        for (int r = r0; r < r1 && b; r++) {
+            const double *row = g + (size_t)r * h->ncols;
+            for (int c = 0; c < h->ncols; c++) {
+                if (cap - u < 400) { /* "%f" of a huge double can take ~320 characters */
+                    cap = cap * 2 + 1024;
+                    char *nb = realloc(b, cap);
+                    if (!nb) { free(b); b = NULL; break; }
+                    b = nb;
+                }
+                u += (size_t)snprintf(b + u, cap - u, "%f ", row[c]);
+            }
+            if (b) b[u++] = '\n';
+        }
+        bufs[t] = b;
+        used[t] = u;
+        if (!b && r1 > r0) {
+#pragma omp atomic write
+            failed = 1;
+        }
     }
-    return fclose(f);
+    for (int t = 0; t < nt && !failed; t++)
+        if (bufs[t] && fwrite(bufs[t], 1, used[t], f) != used[t]) failed = 1;
+    if (bufs) for (int t = 0; t < nt; t++) free(bufs[t]);
+    free(bufs);
+    free(used);
+    if (fclose(f) != 0) failed = 1;
+    return failed ? -1 : 0;
 }
 
 /* ---- run ------------------------------------------------------------------- */
@@ -338,6 +418,14 @@ int main(int argc, char **argv)
     if (argc == 1) {
         usage_all();
         return EXIT_USAGE;
+    }
+    if (argc == 4 && !strcmp(argv[1], "--asc-roundtrip")) { /* test hook: read a grid, write it back */
+        char *hb0 = slurp(argv[2], NULL);
+        asc_header h0;
+        if (!hb0 || !parse_header(hb0, &h0)) return 1;
+        free(hb0);
+        double *g0 = read_grid(argv[2], h0.nrows, h0.ncols, 0.0, NULL);
+        return (g0 && write_grid(argv[3], &h0, g0) == 0) ? 0 : 1;
     }
     if (argc == 2) {
         if (is_module(argv[1])) {
