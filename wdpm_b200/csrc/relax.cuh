@@ -90,13 +90,44 @@ WDPM_HD void tile_store(const Tile<T>& t, T* w0, T* w1, T* w2, int j) {
     w2[j - 1] = t.wn[5]; w2[j] = t.wn[6]; w2[j + 1] = t.wn[7];
 }
 
+// mini(a, b) = (a <= b) ? a : b (runoff.cl:14-22). For fp32 on the device the single-instruction
+// fminf is used instead: it differs only for NaN operands and for zeros of opposite sign, neither
+// of which can reach this call (b = the centre's water is never -0; a = -0 would need a four-term
+// flow of (-0)+(-0), and x-x is +0).
+template <typename T>
+WDPM_HD T mini(T a, T b) {
+#ifdef __CUDA_ARCH__
+    if (sizeof(T) == 4) return (T)fminf((float)a, (float)b);
+#endif
+    return (a <= b) ? a : b;
+}
+
+// if (take) { wc -= flow; wn += flow; }
+// fp32, device: two predicated round-to-nearest adds in PTX (left to itself the compiler turns the
+// `if` into add + select per operand). fp64: ptxas turns predicated DADDs back into selects, so the
+// cheapest form is ONE select of the amount moved - when nothing moves the amount is -0.0, the
+// additive identity that preserves even a negative zero in wn (x + -0.0 == x bit for bit) and
+// leaves wc unchanged (wc is never negative nor -0 for an active centre).
+template <typename T>
+WDPM_HD void move_if(bool take, T& wc, T& wn, T flow) {
+#ifdef __CUDA_ARCH__
+    if (sizeof(T) == 4) {
+        float c = (float)wc, n = (float)wn;
+        asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p sub.rn.f32 %0, %0, %3;\n\t@p add.rn.f32 %1, %1, %3;\n\t}"
+            : "+f"(c), "+f"(n) : "r"((int)take), "f"((float)flow));
+        wc = (T)c; wn = (T)n;
+        return;
+    }
+#endif
+    const T give = take ? flow : T(-0.0);
+    wc = wc - give;
+    wn = wn + give;
+}
+
 // One neighbour step, branch-free. wc is the centre's running water.
 //
-// The reference does  flow = mini(flow, wc); wc -= flow; wn += flow  under `if (h > 0)`.
-// Here the `if` becomes a select of the amount given: when h <= 0 the amount is -0.0, the
-// additive identity that preserves even a negative zero in wn (x + -0.0 == x bit for bit) and
-// leaves wc unchanged (wc is never negative nor -0 for an active centre). The capped case gives
-// wc itself, so wc - wc = +0 exactly as in the reference.
+// The reference does  flow = mini(flow, wc); wc -= flow; wn += flow  under `if (h > 0)`; here
+// the flow is computed unconditionally and only the two updates depend on h > 0 (move_if).
 template <typename T, int MODULE>
 WDPM_HD void push(T dc, T& wc, T dn, T& wn) {
     const T sn = dn + wn;
@@ -108,11 +139,8 @@ WDPM_HD void push(T dc, T& wc, T dn, T& wn) {
     else x = (dc > sn) ? wc : ((dc - dn) + (wc - wn));
     T flow = x * T(0.125);
     if (MODULE == kDrain) flow = (flow <= T(0)) ? T(0) : flow;
-    const bool fits = flow <= wc;
-    const T other = pos ? wc : T(-0.0);   // known before the multiply: off the dependent chain
-    const T give = (pos && fits) ? flow : other;
-    wc = wc - give;
-    wn = wn + give;
+    flow = mini(flow, wc);  // runoff.cl:46
+    move_if(pos, wc, wn, flow);
 }
 
 // The same eight steps on a register window that slides one column per colour sub-pass:
