@@ -476,8 +476,16 @@ k_fused(const FusedParams<T> p) {
         if (any) bulk_commit();
     };
 
+    // Barriers. The colour sub-steps of a step only order tiles of the SAME row triple (they exchange
+    // window columns); different row groups touch disjoint rows within a step. When every row group
+    // is a whole number of warps and each thread owns one tile (GROUPED), the two inner barriers are
+    // named barriers over one row group only, so the groups drift apart inside a step and their
+    // load / compute / store bursts interleave; the whole CTA (and the data-movement warp) meets
+    // once per step. Otherwise all three are block barriers.
+    constexpr bool GROUPED = (CFG::NCP % 32 == 0) && (NPH * NT * CFG::NCP == NTHREADS) && (NPH * NT <= 15);
+
     // Warp specialisation: the last warp only moves data (one elected lane issues the bulk copies),
-    // the first NTHREADS threads only compute. Both sides meet at the three block barriers of a step.
+    // the first NTHREADS threads only compute.
     if (tid >= NTHREADS) {
         const bool lead = tid == NTHREADS;
         if (lead)
@@ -493,8 +501,10 @@ k_fused(const FusedParams<T> p) {
                 if (s + PF < tile.n_steps) issue_loads(s + PF);
             }
             __syncwarp();
-            __syncthreads();
-            __syncthreads();
+            if (!GROUPED) {
+                __syncthreads();
+                __syncthreads();
+            }
             __syncthreads();
         }
         if (lead) {
@@ -620,10 +630,14 @@ k_fused(const FusedParams<T> p) {
                 }
             }
         };
+        auto group_barrier = [&]() {
+            if (GROUPED) asm volatile("bar.sync %0, %1;" ::"r"(1 + tid / CFG::NCP), "n"(CFG::NCP) : "memory");
+            else __syncthreads();
+        };
         substep(std::integral_constant<int, 0>{});
-        __syncthreads();
+        group_barrier();
         substep(std::integral_constant<int, 1>{});
-        __syncthreads();
+        group_barrier();
         substep(std::integral_constant<int, 2>{});
         fence_proxy_async();  // make this step's smem writes visible to the bulk-store engine
         __syncthreads();
