@@ -122,6 +122,9 @@ const std::vector<FusedVariant<float>>& fused_variants<float>() {
         make_variant<float, MwCfg<640, 2, 1, 1>, 640, 1>(),    // 8: two triples per phase, two tiles per thread
         make_variant<float, MwCfg<768, 2, 1, 1>, 512, 1>(),    // 9: two triples per phase, three tiles per thread
         make_variant<float, MwCfg<384, 2, 1, 1>, 768, 2>(),    // 10: two CTAs of 24 warps per SM
+        make_variant<float, MwCfg<580, 1, 1, 2>, 576, 2>(),    // 11: 192 tiles per row group (whole warps), two CTAs per SM
+        make_variant<float, MwCfg<484, 1, 1, 2>, 480, 2>(),    // 12: 160 tiles per row group, two CTAs per SM
+        make_variant<float, MwCfg<772, 2, 1, 1>, 768, 1>(),    // 13: 256 tiles per row group... one CTA per SM
     };
     return v;
 }
