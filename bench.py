@@ -405,7 +405,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--sample-size", type=int, default=2048)
-    ap.add_argument("--ref-iters-per-step", type=int, default=20)
+    ap.add_argument("--ref-iters-per-step", type=int, default=100)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
