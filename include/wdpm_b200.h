@@ -49,6 +49,7 @@ extern "C" {
 #define WDPM_KERNEL_AUTO 0
 #define WDPM_KERNEL_COLOUR 1 /* one launch per colour sub-pass, global memory (the reference's schedule) */
 #define WDPM_KERNEL_FUSED 2  /* one launch per iteration: 9 sub-passes over a TMA-fed shared-memory row window */
+#define WDPM_KERNEL_RESIDENT 3 /* small grids: one cooperative launch per block, tiles resident in shared memory */
 
 /* error codes */
 #define WDPM_OK 0

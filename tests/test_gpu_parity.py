@@ -48,6 +48,24 @@ def test_colour_kernel_matches_oracle(cuda_lib, oracle, dt, mn, mod):
             assert dt(ta) == dt(tb)
 
 
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("mn,mod", MODS)
+def test_resident_kernel_matches_oracle(cuda_lib, oracle, dt, mn, mod):
+    """The small-grid kernel: one cooperative launch for all iterations, tiles resident in shared memory."""
+    from wdpm_b200 import KERNEL_RESIDENT
+    rng = np.random.default_rng(23)
+    for rows, cols, n in ((1, 1, 3), (2, 7, 4), (33, 65, 25), (100, 131, 25), (257, 190, 12), (482, 471, 7), (40, 900, 8)):
+        D, W = random_case(rng, rows, cols, dt)
+        outlet = oracle.find_outlet(D) or (1, 1)
+        a = W.copy()
+        ta = oracle.iterate(a, D, NODATA, mod, n, outlet=outlet, totaldrain=0.5)
+        b, tb, info = _cuda_iterate(cuda_lib, D, W, mod, dt, n, outlet=outlet, td=0.5, kernel=KERNEL_RESIDENT)
+        assert info["kernel"] == KERNEL_RESIDENT
+        assert np.array_equal(a, b), (rows, cols, int((a != b).sum()))
+        if mod == 2:
+            assert dt(ta) == dt(tb)
+
+
 def _variants(dtype_code):
     from wdpm_b200 import solver
     v, out = 1, []
@@ -191,7 +209,7 @@ def test_basin5_fused_kernel_equals_colour_kernel(cuda_lib, basin5):
     from wdpm_b200 import F64, KERNEL_COLOUR, KERNEL_FUSED, Solver
     hdr, dem = basin5
     res = []
-    for kernel, variant in ((KERNEL_COLOUR, 0), (KERNEL_FUSED, 1), (KERNEL_FUSED, 5), (KERNEL_FUSED, 6), (KERNEL_FUSED, 0)):
+    for kernel, variant in ((KERNEL_COLOUR, 0), (KERNEL_FUSED, 1), (KERNEL_FUSED, 5), (KERNEL_FUSED, 6), (KERNEL_FUSED, 0), (3, 0), (0, 0)):
         s = Solver(hdr.nrows, hdr.ncols, hdr.nodata, 0, dtype=F64, zero_threshold=5e-6, kernel=kernel, fused_variant=variant)
         s.upload(dem, None)
         s.apply_add(0.3, 1.0)
@@ -203,7 +221,7 @@ def test_basin5_fused_kernel_equals_colour_kernel(cuda_lib, basin5):
         assert r == res[0][1]
 
 
-@pytest.mark.parametrize("dt,size", [(np.float32, 8192), (np.float64, 4096)])
+@pytest.mark.parametrize("dt,size", [(np.float32, 8192), (np.float64, 4096), (np.float64, 32768)])
 def test_large_grid_properties(cuda_lib, dt, size):
     """Sizes the oracle cannot reach in seconds: the fused kernel must equal the colour kernel bit for
     bit (two independent CUDA code paths), conserve mass to rounding, keep margins dry and be a no-op
@@ -211,10 +229,14 @@ def test_large_grid_properties(cuda_lib, dt, size):
     import torch
     from oracle import pyoracle
     from wdpm_b200 import F32, F64, KERNEL_COLOUR, KERNEL_FUSED, Solver, synth
+    if size >= 32768:  # BASELINE.json's full size: 35 GB on the device, ~30 GB of host arrays
+        import psutil
+        if torch.cuda.get_device_properties(0).total_memory < 100e9 or psutil.virtual_memory().available < 60e9:
+            pytest.skip("not enough memory for the 32768^2 case")
     code = F64 if dt == np.float64 else F32
     dem = synth.fractal_dem(size, size, seed=size, device="cuda", dtype=torch.float64)
     dem = (dem - dem.min()).to(torch.float32 if dt == np.float32 else torch.float64).cpu().numpy()
-    n_it = 6
+    n_it = 6 if size < 32768 else 3
     outs = []
     for kernel in (KERNEL_COLOUR, KERNEL_FUSED):
         s = Solver(size, size, NODATA, 0, dtype=code, kernel=kernel)

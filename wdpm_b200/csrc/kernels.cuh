@@ -14,6 +14,7 @@
 
 #include <cstdint>
 #include <type_traits>
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include "mw_schedule.h"
@@ -643,6 +644,108 @@ k_fused(const FusedParams<T> p) {
         __syncthreads();
 
     }
+}
+
+// ---------------------------------------------------------------------------
+// Resident kernel: grids of up to about a million cells (the reference's own DEMs: basin5 is
+// 482 x 471). Such a grid cannot amortise a launch per iteration, nor fill 148 SMs with marching
+// windows; what bounds an iteration is the LATENCY of nine dependent colour sub-passes. So the whole
+// block of n iterations is ONE cooperative launch: every CTA owns a TR x TC tile of the padded grid,
+// keeps its elevations in shared memory for the whole launch, and per iteration reads its tile plus
+// halo (3 rows above, 6 below, 9 columns left, 18 right: what a whole iteration consumes, see
+// mw_schedule.h) from the current water buffer - L2 resident at these sizes -, runs the nine
+// sub-passes on it with block barriers, writes its owned cells to the other buffer and meets the
+// other CTAs at a grid barrier. Tiles partly outside the shared-memory tile are skipped; the cells
+// they would have produced lie in the halo and are never written back.
+// ---------------------------------------------------------------------------
+
+constexpr int kResHaloTop = 3, kResHaloBottom = 6, kResHaloLeft = 9, kResHaloRight = 18;
+
+template <typename T>
+struct ResidentParams {
+    T* w[2];        // ping / pong; w[cur] holds the state on entry
+    const T* dem;
+    Geom g;
+    int cur;
+    int TR, TC;     // owned rows / cols per CTA (multiples of 3)
+    int n_tx;       // CTAs per grid row
+    int n_iters;
+    int launch_parity;  // drain event buffer of the first iteration
+    DrainState<T> ds;
+};
+
+template <typename T, int MODULE, int NTHREADS>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_resident(const ResidentParams<T> p) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int SR = p.TR + kResHaloTop + kResHaloBottom, SC = p.TC + kResHaloLeft + kResHaloRight;
+    T* sw = reinterpret_cast<T*>(smem_raw);  // [SR][SC] water
+    T* sd = sw + SR * SC;                    // [SR][SC] masked elevations
+    const int tid = threadIdx.x;
+    const int ty = blockIdx.x / p.n_tx, tx = blockIdx.x % p.n_tx;
+    const int r_own = ty * p.TR, c_own = tx * p.TC;                  // padded coordinates of the owned tile
+    const int r0 = r_own - kResHaloTop, c0 = c_own - kResHaloLeft;   // ... and of the shared-memory tile
+    const size_t pitch = (size_t)p.g.pitch;
+    const size_t base = (size_t)(r0 + kPadTop) * pitch + (size_t)(c0 + kPadLeft);
+
+    for (int k = tid; k < SR * SC; k += NTHREADS) {
+        const int i = k / SC, j = k - i * SC;
+        sd[k] = p.dem[base + (size_t)i * pitch + j];
+    }
+    int cur = p.cur, parity = p.launch_parity;
+    for (int it = 0; it < p.n_iters; it++) {
+        const T* __restrict__ win = p.w[cur];
+        T* __restrict__ wout = p.w[cur ^ 1];
+        if (MODULE == kDrain && blockIdx.x == 0 && tid == 0) fold_events(p.ds, parity ^ 1);
+        for (int k = tid; k < SR * SC; k += NTHREADS) {
+            const int i = k / SC, j = k - i * SC;
+            sw[k] = win[base + (size_t)i * pitch + j];
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int sub = 0; sub < 9; sub++) {
+            const int oi = sub / 3, oj = sub - 3 * oi;       // tile-start offsets = (reference oi, oj) - 1
+            const int na = (SR - 3 - oi) / 3 + 1, nb = (SC - 3 - oj) / 3 + 1;
+            for (int k = tid; k < na * nb; k += NTHREADS) {
+                const int a = k / nb, b = k - a * nb;
+                const int i = oi + 3 * a, j = oj + 3 * b + 1;  // tile's first row, centre column
+                T* w0 = sw + i * SC; T* w1 = w0 + SC; T* w2 = w1 + SC;
+                const T* d0 = sd + i * SC; const T* d1 = d0 + SC; const T* d2 = d1 + SC;
+                if (MODULE == kDrain) {
+                    const int crow = r0 + i + 1, ccol = c0 + j;
+                    const int orow = p.ds.drainrow - crow, ocol = p.ds.draincol - ccol;
+                    if (orow >= -1 && orow <= 1 && ocol >= -1 && ocol <= 1) {
+                        if (orow != 0 || ocol != 0) {
+                            T evo, evc;
+                            bool drained;
+                            relax_tile_at_outlet<T>(w0, w1, w2, d0, d1, d2, j, orow, ocol, &evo, &evc, &drained);
+                            // only the CTA that owns the centre reports the contact (halo copies recompute it)
+                            if (drained && crow >= r_own && crow < r_own + p.TR && ccol >= c_own && ccol < c_own + p.TC) {
+                                DrainEvent<T>* ev = p.ds.events + parity * kEventsPerBuffer + sub;
+                                ev->w_outlet = evo;
+                                ev->w_centre = evc;
+                                ev->valid = 1;
+                            }
+                        }
+                        continue;
+                    }
+                }
+                relax_tile<T, MODULE>(w0, w1, w2, d0, d1, d2, j);
+            }
+            __syncthreads();
+        }
+        for (int k = tid; k < p.TR * p.TC; k += NTHREADS) {
+            const int i = k / p.TC, j = k - i * p.TC;
+            wout[(size_t)(r_own + i + kPadTop) * pitch + (size_t)(c_own + j + kPadLeft)] =
+                sw[(i + kResHaloTop) * SC + j + kResHaloLeft];
+        }
+        grid.sync();
+        cur ^= 1;
+        parity ^= 1;
+    }
+    if (MODULE == kDrain && blockIdx.x == 0 && tid == 0) fold_events(p.ds, parity ^ 1);
 }
 
 }  // namespace wdpm

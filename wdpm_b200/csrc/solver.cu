@@ -143,6 +143,10 @@ struct wdpm_solver {
     int n_strips = 0, total_triples = 0, chunk_triples = 0, n_chunks = 0;
     int sm_count = 0;
     int device = 0;
+    // resident kernel tiling (kernels.cuh, k_resident); res_ok = the grid fits one co-resident wave
+    bool res_ok = false;
+    int res_TR = 0, res_TC = 0, res_ntx = 0, res_nty = 0;
+    size_t res_smem = 0;
 
     void* dem = nullptr;
     void* w[2] = {nullptr, nullptr};
@@ -314,8 +318,47 @@ int fused_launch_only(wdpm_solver* s) {
     return WDPM_OK;
 }
 
+constexpr int kResidentThreads = 512;
+
+template <typename T, int MODULE>
+cudaError_t launch_resident(wdpm_solver* s, int n) {
+    ResidentParams<T> p;
+    p.w[0] = static_cast<T*>(s->w[0]);
+    p.w[1] = static_cast<T*>(s->w[1]);
+    p.dem = static_cast<const T*>(s->dem);
+    p.g = s->g;
+    p.cur = s->cur;
+    p.TR = s->res_TR;
+    p.TC = s->res_TC;
+    p.n_tx = s->res_ntx;
+    p.n_iters = n;
+    p.launch_parity = s->launch_parity;
+    p.ds = drain_state<T>(s);
+    void* args[] = {&p};
+    auto kern = k_resident<T, MODULE, kResidentThreads>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->res_smem);
+    if (e != cudaSuccess) return e;
+    return cudaLaunchCooperativeKernel((void*)kern, dim3(s->res_ntx * s->res_nty), dim3(kResidentThreads), args, s->res_smem, s->stream);
+}
+
+template <typename T>
+int resident_iterations(wdpm_solver* s, int n) {
+    if (n <= 0) return WDPM_OK;
+    cudaError_t e;
+    switch (s->module) {
+        case WDPM_ADD: e = launch_resident<T, kAdd>(s, n); break;
+        case WDPM_SUBTRACT: e = launch_resident<T, kSubtract>(s, n); break;
+        default: e = launch_resident<T, kDrain>(s, n); break;
+    }
+    CUDA_TRY(e);
+    s->launches++;
+    if (n & 1) { s->cur ^= 1; s->launch_parity ^= 1; }
+    return WDPM_OK;
+}
+
 template <typename T>
 int iterate_t(wdpm_solver* s, int n) {
+    if (s->kernel == WDPM_KERNEL_RESIDENT) return resident_iterations<T>(s, n);
     if (s->kernel == WDPM_KERNEL_FUSED) return fused_iterations<T>(s, n);
     return colour_iterations<T>(s, n);
 }
@@ -458,7 +501,7 @@ int wdpm_create(const wdpm_config* cfg, wdpm_solver** out) {
     if (cfg->rows < 1 || cfg->cols < 1) return fail(WDPM_E_ARG, "rows and cols must be positive");
     if (cfg->dtype != WDPM_F32 && cfg->dtype != WDPM_F64) return fail(WDPM_E_ARG, "dtype must be WDPM_F32 or WDPM_F64");
     if (cfg->module < WDPM_ADD || cfg->module > WDPM_DRAIN) return fail(WDPM_E_ARG, "unknown module");
-    if (cfg->kernel < WDPM_KERNEL_AUTO || cfg->kernel > WDPM_KERNEL_FUSED) return fail(WDPM_E_ARG, "unknown kernel selector");
+    if (cfg->kernel < WDPM_KERNEL_AUTO || cfg->kernel > WDPM_KERNEL_RESIDENT) return fail(WDPM_E_ARG, "unknown kernel selector");
     const bool is_stripe = cfg->stripe_rows > 0;
     if (is_stripe) {
         if (cfg->stripe_row0 < 0 || cfg->stripe_row0 % 3 != 0) return fail(WDPM_E_ARG, "stripe_row0 must be a non-negative multiple of 3");
@@ -540,7 +583,43 @@ int wdpm_create(const wdpm_config* cfg, wdpm_solver** out) {
     s->total_triples = (s->P + 2) / 3;
     s->g.pitch = ((kPadLeft + s->n_strips * TWV + (W - TWV - HL) + 31) / 32) * 32;
     s->g.nrows_dev = kPadTop + 3 * (s->total_triples + 2 * kMaxItersPerLaunch) + 3;
+    {   // room for the resident kernel's tiles (whole tiles + halo, whatever tiling is chosen below)
+        const int extra_cols = kPadLeft + (cfg->cols + 2) + (cfg->cols + 2) / 2 + 64;
+        const int extra_rows = kPadTop + (s->P) + (s->P) / 2 + 32;
+        if ((long long)(cfg->rows + 2) * (cfg->cols + 2) <= (1ll << 21)) {
+            s->g.pitch = std::max(s->g.pitch, ((extra_cols + 31) / 32) * 32);
+            s->g.nrows_dev = std::max(s->g.nrows_dev, extra_rows);
+        }
+    }
     choose_chunks(s, K, NT, minb, cfg->fused_chunk_rows);
+
+    // resident tiling: at most one CTA per SM (cooperative launch), tiles aligned to multiples of 3
+    if (!is_stripe) {
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device);
+        const int PR = cfg->rows + 2, PC = cfg->cols + 2;
+        long long best = -1;
+        for (int ntx = 1; ntx <= s->sm_count && coop; ntx++) {
+            const int nty_max = s->sm_count / ntx;
+            if (nty_max < 1) break;
+            const int TC = 3 * ((((PC + ntx - 1) / ntx) + 2) / 3);
+            const int nty = std::min(nty_max, std::max(1, (PR + 2) / 3));
+            const int TR = 3 * ((((PR + nty - 1) / nty) + 2) / 3);
+            const int real_ntx = (PC + TC - 1) / TC, real_nty = (PR + TR - 1) / TR;
+            const long long cost = (long long)(TR + kResHaloTop + kResHaloBottom) * (TC + kResHaloLeft + kResHaloRight);
+            if (best < 0 || cost < best) {
+                best = cost;
+                s->res_TR = TR; s->res_TC = TC; s->res_ntx = real_ntx; s->res_nty = real_nty;
+            }
+        }
+        if (best > 0) {
+            s->res_smem = (size_t)2 * best * s->esize;
+            // a thread should own at most a few tiles per sub-pass, and the tile must fit shared memory
+            s->res_ok = s->res_smem <= 200 * 1024 && best <= 9ll * 4 * kResidentThreads && cells <= (1ll << 21);
+        }
+    }
+    if (cfg->kernel == WDPM_KERNEL_RESIDENT && !s->res_ok) { delete s; return fail(WDPM_E_UNSUPPORTED, "grid too large (or device unsuitable) for the resident kernel"); }
+    if (cfg->kernel == WDPM_KERNEL_AUTO && s->res_ok && cells <= (1ll << 20)) s->kernel = WDPM_KERNEL_RESIDENT;
 
     auto cleanup = [&](int code, const std::string& msg) {
         wdpm_destroy(s);
@@ -818,6 +897,15 @@ int wdpm_get_info(wdpm_solver* s, wdpm_info* info) {
     info->cta_threads = nt;
     info->smem_bytes = (int32_t)smem;
     info->iters_per_launch = s->kernel == WDPM_KERNEL_FUSED ? K : 1;
+    if (s->kernel == WDPM_KERNEL_RESIDENT) {  // the resident kernel's tiling instead
+        info->strip_cols = s->res_TC;
+        info->window_cols = s->res_TC + kResHaloLeft + kResHaloRight;
+        info->chunk_rows = s->res_TR;
+        info->grid_ctas = s->res_ntx * s->res_nty;
+        info->cta_threads = kResidentThreads;
+        info->smem_bytes = (int32_t)s->res_smem;
+        info->iters_per_launch = 0;  // a whole block of iterations per launch
+    }
     return WDPM_OK;
 }
 

@@ -15,7 +15,7 @@ import numpy as np
 
 ADD, SUBTRACT, DRAIN = 0, 1, 2
 F32, F64 = 0, 1
-KERNEL_AUTO, KERNEL_COLOUR, KERNEL_FUSED = 0, 1, 2
+KERNEL_AUTO, KERNEL_COLOUR, KERNEL_FUSED, KERNEL_RESIDENT = 0, 1, 2, 3
 MODULES = {"add": ADD, "subtract": SUBTRACT, "drain": DRAIN}
 
 _PKG = Path(__file__).resolve().parent
