@@ -202,8 +202,15 @@ WDPM_HD bool relax_tile(T* w0, T* w1, T* w2, const T* d0, const T* d1, const T* 
 //   totaldrain = totaldrain + w[outlet] + w[centre]; both set to 0; the walk goes on.
 // The two addends are returned so the caller can fold them into totaldrain in
 // sub-pass order: *ev_outlet = w[outlet], *ev_centre = w[centre] at that moment.
+// Kept out of line on the device: it runs for at most eight tiles per iteration, and inlining its
+// pointer tables into the hot loop costs every thread registers (and spills).
+#ifdef __CUDACC__
+#define WDPM_RARE __host__ __device__ __noinline__
+#else
+#define WDPM_RARE inline
+#endif
 template <typename T>
-WDPM_HD bool relax_tile_at_outlet(T* w0, T* w1, T* w2, const T* d0, const T* d1, const T* d2, int j,
+WDPM_RARE bool relax_tile_at_outlet(T* w0, T* w1, T* w2, const T* d0, const T* d1, const T* d2, int j,
                                   int orow, int ocol, T* ev_outlet, T* ev_centre, bool* drained) {
     *drained = false;
     T wc = w1[j];

@@ -19,6 +19,7 @@ namespace {
 
 constexpr int kDefaultVariantF64 = 10;  // 384-column window, two row triples per phase, 24 compute warps
 constexpr int kDefaultVariantF32 = 7;   // 512-column window, two CTAs of 16 compute warps per SM
+constexpr int kDefaultVariantF64Drain = 1;  // Drain's relax step needs more registers than 24 warps leave: 16 warps, 512 columns
 // Grids of a few hundred thousand cells (the reference's basin5 is 482 x 471) cannot fill 148 SMs
 // with long chunks: narrow windows, two CTAs per SM and chunks of a few row triples spread the
 // rows over the whole chip in one wave (measured on basin5: 18 us per iteration against 37 us for
@@ -546,7 +547,7 @@ int wdpm_create(const wdpm_config* cfg, wdpm_solver** out) {
     int variant = cfg->fused_variant;
     if (variant < 0 || variant > nvar) { delete s; return fail(WDPM_E_ARG, "fused_variant out of range"); }
     if (variant == 0) {
-        variant = s->dtype == WDPM_F64 ? kDefaultVariantF64 : kDefaultVariantF32;
+        variant = s->dtype == WDPM_F64 ? (cfg->module == WDPM_DRAIN ? kDefaultVariantF64Drain : kDefaultVariantF64) : kDefaultVariantF32;
         if (cells < kSmallGridCells && !is_stripe) variant = s->dtype == WDPM_F64 ? kSmallGridVariantF64 : kSmallGridVariantF32;
         if (cfg->iters_per_launch > 1) {
             variant = 0;
