@@ -14,10 +14,9 @@
 // have skipped the neighbour: the validity compare and its branch disappear
 // from the inner loop. A centre is valid iff its elevation is finite.
 //
-// The step is written branch-free (selects / predicated adds) against a
-// register-resident tile so that several tiles can be relaxed interleaved by
-// one thread: the eight neighbour steps of a tile form one dependent chain,
-// and interleaving independent chains is what keeps the FP pipes busy.
+// The step is written branch-free (selects / predicated adds) against
+// register-resident values: the eight neighbour steps of a tile form one
+// dependent chain, and anything that lengthens it costs directly.
 //
 // The functions are __host__ __device__ so the schedule emulator in tests/ can
 // run the very same arithmetic on the CPU; the product never calls them there.
@@ -168,21 +167,6 @@ WDPM_HD void tile_relax(Tile<T>& t) {
 #pragma unroll
 #endif
     for (int n = 0; n < 8; n++) push<T, MODULE>(t.dc, t.wc, t.dn[n], t.wn[n]);
-}
-
-// N independent tiles, neighbour step by neighbour step, so the compiler
-// interleaves the N dependent chains.
-template <typename T, int MODULE, int N>
-WDPM_HD void tiles_relax(Tile<T> (&t)[N]) {
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-    for (int n = 0; n < 8; n++) {
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-        for (int k = 0; k < N; k++) push<T, MODULE>(t[k].dc, t[k].wc, t[k].dn[n], t[k].wn[n]);
-    }
 }
 
 // Convenience: load, relax if active, store. Returns whether work was done.
