@@ -138,6 +138,14 @@ int wdpm_get_cell_water(wdpm_solver *s, int32_t row, int32_t col, double *value)
  * max-difference and sum (:1239-1268). The reference always passes 1000. */
 int wdpm_run_block(wdpm_solver *s, int32_t n_iters, wdpm_block_result *out);
 
+/* The same block in pieces, for a host thread that drives several stripe solvers (one per GPU):
+ * begin = threshold + snapshot, enqueue = n more iterations, end = reductions + the only host wait.
+ * begin and enqueue never block, so the host can feed all stripes round-robin; their kernels find
+ * each other through the device-side halo flags. wdpm_run_block = begin + enqueue(n) + end. */
+int wdpm_block_begin(wdpm_solver *s);
+int wdpm_block_enqueue(wdpm_solver *s, int32_t n_iters);
+int wdpm_block_end(wdpm_solver *s, wdpm_block_result *out);
+
 /* n_iters iterations only - no threshold, snapshot or reductions (benchmarks, tests). */
 int wdpm_iterate(wdpm_solver *s, int32_t n_iters);
 /* a single colour sub-pass (oi, oj in 1..3), colour kernel only (tests). */

@@ -117,3 +117,27 @@ def test_asc_reader_parses_the_dem_like_strtod(host_bin, tmp_path):
     h1, b = ascgrid.read_asc(out)
     assert (h0.ncols, h0.nrows, h0.cellsize, h0.nodata) == (h1.ncols, h1.nrows, h1.cellsize, h1.nodata)
     assert np.array_equal(np.round(a, 6), b)  # "%f" keeps six decimals; the DEM has four
+
+
+@pytest.mark.gpu
+def test_binary_on_several_gpus_gives_the_same_files(host_bin, tmp_path):
+    """WDPM_B200_GPUS=N: one host thread drives N stripe solvers (begin / enqueue / end); the validation
+    sequence must still reproduce the reference's files byte for byte."""
+    import os
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs (run under gpurun --gpus 2)")
+    env = dict(os.environ, WDPM_B200_GPUS=str(min(n, 4)))
+    dem = gunzip_to("basin5.asc.gz", tmp_path / "basin5.asc")
+    add, drain, sub = tmp_path / "add.asc", tmp_path / "drain.asc", tmp_path / "sub.asc"
+    runs = [
+        ("add10", ["add", dem, "NULL", add, "NULL", "10", "1.0", "1.0", "1", "1", "0.005", "0"], add),
+        ("drain", ["drain", dem, add, drain, "NULL", "0.1", "1.0", "1", "1", "0.005", "0"], drain),
+        ("sub10", ["subtract", dem, drain, sub, "NULL", "10", "1.0", "1", "1", "0.005", "0"], sub),
+    ]
+    for name, argv, out in runs:
+        res = subprocess.run([str(host_bin)] + [str(a) for a in argv], capture_output=True, text=True, timeout=900, env=env)
+        assert res.returncode == 0, res.stdout[-800:] + res.stderr
+        assert out.read_text() == golden_text(f"ref_opencl_{name}.asc.gz"), name
+        assert _normalise(res.stdout) == _normalise((GOLDEN / f"ref_opencl_{name}.txt").read_text()), name

@@ -186,6 +186,10 @@ struct wdpm_solver {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     long long launches = 0;
     long long device_bytes = 0;
+    // state of an open block (wdpm_block_begin .. wdpm_block_end)
+    bool in_block = false;
+    long long blk_launches0 = 0;
+    int blk_iters = 0;
 };
 
 namespace {
@@ -368,10 +372,12 @@ int iterate(wdpm_solver* s, int n) {
     return s->dtype == WDPM_F64 ? iterate_t<double>(s, n) : iterate_t<float>(s, n);
 }
 
+// A block in three non-blocking-then-blocking pieces (see wdpm_block_begin/enqueue/end).
 template <typename T>
-int run_block_t(wdpm_solver* s, int n_iters, wdpm_block_result* out) {
+int block_begin_t(wdpm_solver* s) {
     const long long n = s->g.cells_dev();
-    const long long launches0 = s->launches;
+    s->blk_launches0 = s->launches;
+    s->blk_iters = 0;
     CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
     if (s->stripe && s->epoch > 0 && (s->above.present || s->below.present)) {
         // the neighbours' last halo push must land before the threshold pass touches the halo rows
@@ -383,8 +389,12 @@ int run_block_t(wdpm_solver* s, int n_iters, wdpm_block_result* out) {
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(s->ev[1], s->stream));
-    int rc = iterate_t<T>(s, n_iters);
-    if (rc) return rc;
+    s->in_block = true;
+    return WDPM_OK;
+}
+
+template <typename T>
+int block_end_t(wdpm_solver* s, wdpm_block_result* out) {
     CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
     k_block_reduce_stage1<T, 256><<<s->reduce_blocks, 256, 0, s->stream>>>(
         static_cast<const T*>(s->w[s->cur]), static_cast<const T*>(s->oldw), static_cast<const T*>(s->dem), s->g, s->partials);
@@ -396,17 +406,28 @@ int run_block_t(wdpm_solver* s, int n_iters, wdpm_block_result* out) {
     CUDA_TRY(cudaMemcpyAsync(&td, s->totaldrain, sizeof(T), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->in_block = false;
     if (out) {
         out->max_diff = s->h_result->max_diff;
         out->masked_sum = s->h_result->sum;
         out->wet_cells = (int64_t)s->h_result->wet;
         out->total_drain = (double)td;
-        out->iterations = n_iters;
-        out->launches = (int32_t)(s->launches - launches0);
+        out->iterations = s->blk_iters;
+        out->launches = (int32_t)(s->launches - s->blk_launches0);
         CUDA_TRY(cudaEventElapsedTime(&out->block_ms, s->ev[0], s->ev[3]));
         CUDA_TRY(cudaEventElapsedTime(&out->iterate_ms, s->ev[1], s->ev[2]));
     }
     return WDPM_OK;
+}
+
+template <typename T>
+int run_block_t(wdpm_solver* s, int n_iters, wdpm_block_result* out) {
+    int rc = block_begin_t<T>(s);
+    if (rc) return rc;
+    rc = iterate_t<T>(s, n_iters);
+    if (rc) return rc;
+    s->blk_iters += n_iters;
+    return block_end_t<T>(s, out);
 }
 
 template <typename T>
@@ -862,6 +883,32 @@ int wdpm_run_block(wdpm_solver* s, int32_t n_iters, wdpm_block_result* out) {
     if (s->module == WDPM_DRAIN && !s->have_outlet) return fail(WDPM_E_STATE, "Drain needs an outlet: call wdpm_find_outlet or wdpm_set_outlet");
     CUDA_TRY(cudaSetDevice(s->device));
     return s->dtype == WDPM_F64 ? run_block_t<double>(s, n_iters, out) : run_block_t<float>(s, n_iters, out);
+}
+
+int wdpm_block_begin(wdpm_solver* s) {
+    if (!s) return fail(WDPM_E_ARG, "null solver");
+    if (!s->have_dem) return fail(WDPM_E_STATE, "upload first");
+    if (s->in_block) return fail(WDPM_E_STATE, "a block is already open");
+    if (s->module == WDPM_DRAIN && !s->have_outlet) return fail(WDPM_E_STATE, "Drain needs an outlet: call wdpm_find_outlet or wdpm_set_outlet");
+    CUDA_TRY(cudaSetDevice(s->device));
+    return s->dtype == WDPM_F64 ? block_begin_t<double>(s) : block_begin_t<float>(s);
+}
+
+int wdpm_block_enqueue(wdpm_solver* s, int32_t n_iters) {
+    if (!s) return fail(WDPM_E_ARG, "null solver");
+    if (!s->in_block) return fail(WDPM_E_STATE, "no open block: call wdpm_block_begin");
+    if (n_iters < 0) return fail(WDPM_E_ARG, "negative iteration count");
+    CUDA_TRY(cudaSetDevice(s->device));
+    const int rc = iterate(s, n_iters);
+    if (rc == WDPM_OK) s->blk_iters += n_iters;
+    return rc;
+}
+
+int wdpm_block_end(wdpm_solver* s, wdpm_block_result* out) {
+    if (!s) return fail(WDPM_E_ARG, "null solver");
+    if (!s->in_block) return fail(WDPM_E_STATE, "no open block: call wdpm_block_begin");
+    CUDA_TRY(cudaSetDevice(s->device));
+    return s->dtype == WDPM_F64 ? block_end_t<double>(s, out) : block_end_t<float>(s, out);
 }
 
 int wdpm_iterate(wdpm_solver* s, int32_t n_iters) {

@@ -16,8 +16,10 @@
  * The update schedule is the OpenCL branch's (runoff.cl arithmetic); see DESIGN.md
  * for how that differs from the serial branch in the last bits of Drain/Subtract.
  *
- * Environment: WDPM_B200_DEVICE (CUDA ordinal, default 0), WDPM_B200_KERNEL
- * (0 auto, 1 colour, 2 fused).
+ * Environment: WDPM_B200_DEVICE (first CUDA ordinal, default 0), WDPM_B200_KERNEL
+ * (0 auto, 1 colour, 2 fused, 3 resident), WDPM_B200_GPUS (number of GPUs, default 1:
+ * the DEM is cut into that many row stripes, one solver per GPU, halos exchanged over
+ * NVLink by the library; results do not depend on the count).
  */
 #define _POSIX_C_SOURCE 200809L
 #include <ctype.h>
@@ -403,6 +405,99 @@ static void die_solver(const char *what)
     exit(-1); /* as exitOnFail, WDPMCL.c:225-232 */
 }
 
+/* ---- one solver, or one stripe solver per GPU ------------------------------- */
+
+enum { MAX_GPUS = 16, ENQUEUE_CHUNK = 50 };
+
+typedef struct {
+    int n;                       /* solvers (1 = plain solver, >1 = row stripes) */
+    wdpm_solver *sv[MAX_GPUS];
+    int32_t band_row0[MAX_GPUS], band_rows[MAX_GPUS], owned_row0[MAX_GPUS], owned_rows[MAX_GPUS];
+} solver_set;
+
+static void set_create(solver_set *ss, wdpm_config base, int want)
+{
+    const int rows = base.rows, padded = rows + 2, triples = (padded + 2) / 3;
+    int n = want;
+    if (n > MAX_GPUS) n = MAX_GPUS;
+    if (n > wdpm_device_count() - base.device) n = wdpm_device_count() - base.device;
+    while (n > 1 && triples < 3 * n) n--; /* a stripe needs at least 9 rows */
+    if (n < 1) n = 1;
+    memset(ss, 0, sizeof *ss);
+    ss->n = n;
+    for (int g = 0; g < n; g++) {
+        wdpm_config cfg = base;
+        cfg.device = base.device + g;
+        if (n > 1) { /* bands of padded rows starting at multiples of 3, as equal as possible */
+            const int t0 = (int)((long long)triples * g / n), t1 = (int)((long long)triples * (g + 1) / n);
+            cfg.stripe_row0 = 3 * t0;
+            cfg.stripe_rows = (3 * t1 < padded ? 3 * t1 : padded) - 3 * t0;
+            cfg.kernel = WDPM_KERNEL_FUSED;
+        }
+        if (wdpm_create(&cfg, &ss->sv[g]) != WDPM_OK) {
+            fprintf(stderr, "Couldn't create the CUDA solver: %s\n", wdpm_last_error());
+            exit(1);
+        }
+        if (n > 1) {
+            if (wdpm_stripe_band(ss->sv[g], &ss->band_row0[g], &ss->band_rows[g], &ss->owned_row0[g], &ss->owned_rows[g]) != WDPM_OK)
+                die_solver("query stripe band");
+        } else {
+            ss->band_rows[g] = ss->owned_rows[g] = rows;
+        }
+    }
+    if (n > 1) {
+        static wdpm_stripe_endpoint ep[MAX_GPUS];
+        for (int g = 0; g < n; g++)
+            if (wdpm_stripe_export(ss->sv[g], &ep[g]) != WDPM_OK) die_solver("export stripe");
+        for (int g = 0; g < n; g++)
+            if (wdpm_stripe_connect(ss->sv[g], g > 0 ? &ep[g - 1] : NULL, g + 1 < n ? &ep[g + 1] : NULL) != WDPM_OK)
+                die_solver("connect stripes");
+    }
+}
+
+static void set_upload(solver_set *ss, const double *dem, const double *water, int cols)
+{
+    for (int g = 0; g < ss->n; g++) {
+        const size_t off = (size_t)ss->band_row0[g] * (size_t)cols;
+        const int rc = ss->n == 1 ? wdpm_upload(ss->sv[g], dem, water)
+                                  : wdpm_stripe_upload(ss->sv[g], dem + off, water + off, ss->band_row0[g], ss->band_rows[g]);
+        if (rc != WDPM_OK) die_solver("upload grids");
+    }
+}
+
+static void set_download(solver_set *ss, double *water, int cols)
+{
+    for (int g = 0; g < ss->n; g++)
+        if (wdpm_download_water(ss->sv[g], water + (size_t)ss->owned_row0[g] * (size_t)cols) != WDPM_OK) die_solver("read water");
+}
+
+/* one block of `iters` iterations on every stripe; results combined in stripe order */
+static void set_run_block(solver_set *ss, int iters, wdpm_block_result *out)
+{
+    if (ss->n == 1) {
+        if (wdpm_run_block(ss->sv[0], iters, out) != WDPM_OK) die_solver("run block");
+        return;
+    }
+    for (int g = 0; g < ss->n; g++)
+        if (wdpm_block_begin(ss->sv[g]) != WDPM_OK) die_solver("begin block");
+    for (int done = 0; done < iters; done += ENQUEUE_CHUNK) { /* feed all GPUs round-robin: nothing here blocks */
+        const int nit = iters - done < ENQUEUE_CHUNK ? iters - done : ENQUEUE_CHUNK;
+        for (int g = 0; g < ss->n; g++)
+            if (wdpm_block_enqueue(ss->sv[g], nit) != WDPM_OK) die_solver("enqueue iterations");
+    }
+    memset(out, 0, sizeof *out);
+    for (int g = 0; g < ss->n; g++) {
+        wdpm_block_result r;
+        if (wdpm_block_end(ss->sv[g], &r) != WDPM_OK) die_solver("end block");
+        if (r.max_diff > out->max_diff) out->max_diff = r.max_diff;
+        out->masked_sum += r.masked_sum;
+        out->total_drain += r.total_drain;
+        out->wet_cells += r.wet_cells;
+        out->launches += r.launches;
+        out->iterations = r.iterations;
+    }
+}
+
 /* what the scratch file and the Add output hold: water with NODATA cells marked (WDPMCL.c:1336-1344, :1386-1392) */
 static void mark_nodata(double *w, const double *dem, size_t n, double nodata)
 {
@@ -546,25 +641,34 @@ int main(int argc, char **argv)
     cfg.zero_threshold = thres;
     cfg.device = getenv("WDPM_B200_DEVICE") ? atoi(getenv("WDPM_B200_DEVICE")) : 0;
     cfg.kernel = getenv("WDPM_B200_KERNEL") ? atoi(getenv("WDPM_B200_KERNEL")) : WDPM_KERNEL_AUTO;
-    wdpm_solver *sv = NULL;
-    if (wdpm_create(&cfg, &sv) != WDPM_OK) {
-        fprintf(stderr, "Couldn't create the CUDA solver: %s\n", wdpm_last_error());
-        return 1;
-    }
-    if (wdpm_upload(sv, dem, water) != WDPM_OK) die_solver("upload grids");
+    static solver_set ss;
+    set_create(&ss, cfg, getenv("WDPM_B200_GPUS") ? atoi(getenv("WDPM_B200_GPUS")) : 1);
+    set_upload(&ss, dem, water, cols);
     if (!resumed) {
-        if (is_add && wdpm_apply_add(sv, depth, a.runoff_frac) != WDPM_OK) die_solver("add water");
-        if (is_sub && wdpm_apply_subtract(sv, depth) != WDPM_OK) die_solver("subtract water");
+        for (int g = 0; g < ss.n; g++) {
+            if (is_add && wdpm_apply_add(ss.sv[g], depth, a.runoff_frac) != WDPM_OK) die_solver("add water");
+            if (is_sub && wdpm_apply_subtract(ss.sv[g], depth) != WDPM_OK) die_solver("subtract water");
+        }
     }
 
     double total_drain = 0.0;
     if (is_drain) {
         int32_t drow = 0, dcol = 0;
         double minel = 0.0, w_out = 0.0;
-        if (wdpm_find_outlet(sv, &drow, &dcol, &minel) != WDPM_OK) die_solver("locate the drain");
-        if (wdpm_get_cell_water(sv, drow, dcol, &w_out) != WDPM_OK) die_solver("read the drain cell");
+        int owner = -1;
+        for (int g = 0; g < ss.n; g++) { /* every stripe's lowest cell; the lowest, first in row-major order, wins */
+            int32_t r, c;
+            double e;
+            if (wdpm_find_outlet(ss.sv[g], &r, &c, &e) != WDPM_OK) continue; /* no cell above 0 in this stripe */
+            if (owner < 0 || e < minel) { owner = g; drow = r; dcol = c; minel = e; }
+        }
+        if (owner < 0) die_solver("locate the drain");
+        for (int g = 0; g < ss.n; g++)
+            if (wdpm_set_outlet(ss.sv[g], drow, dcol) != WDPM_OK) die_solver("set the drain");
+        if (wdpm_get_cell_water(ss.sv[owner], drow, dcol, &w_out) != WDPM_OK) die_solver("read the drain cell");
         total_drain = w_out > 0 ? w_out : 0; /* WDPMCL.c:1029 */
-        if (wdpm_set_total_drain(sv, total_drain) != WDPM_OK) die_solver("set totaldrain");
+        for (int g = 0; g < ss.n; g++)
+            if (wdpm_set_total_drain(ss.sv[g], g == owner ? total_drain : 0.0) != WDPM_OK) die_solver("set totaldrain");
         line("               ");
         printf("%30s\n", "Basin summary");
         printf("%20s %10.4f %s\n", "Basin area:", (double)basincount * cellarea, "m2");
@@ -590,7 +694,7 @@ int main(int argc, char **argv)
     while (!done) {
         const double old_drain = total_drain;
         wdpm_block_result r;
-        if (wdpm_run_block(sv, BLOCK_ITERATIONS, &r) != WDPM_OK) die_solver("run block");
+        set_run_block(&ss, BLOCK_ITERATIONS, &r);
         k += BLOCK_ITERATIONS;
         total_drain = r.total_drain;
         double diffdrain = 0.0;
@@ -603,14 +707,14 @@ int main(int argc, char **argv)
         }
         done = r.max_diff <= eltol || (is_drain && diffdrain < a.drain_tol) || (a.iter_limit > 0 && k >= a.iter_limit);
         if (!done && !is_null_name(a.scratch)) {
-            if (wdpm_download_water(sv, water) != WDPM_OK) die_solver("read water for the scratch file");
+            set_download(&ss, water, cols);
             if (is_add) mark_nodata(water, dem, n, nodata);
             write_grid(a.scratch, &hdr, water);
         }
     }
 
     /* final grid and statistics (WDPMCL.c:1379-1467) */
-    if (wdpm_download_water(sv, water) != WDPM_OK) die_solver("read water");
+    set_download(&ss, water, cols);
     mark_nodata(water, dem, n, nodata);
     long watercount = 0;
     double watertotal = 0.0;
@@ -646,7 +750,7 @@ int main(int argc, char **argv)
         return 1;
     }
     printf("%20s %10.2f %s\n", "Run Time", seconds_since(&t0), "s");
-    wdpm_destroy(sv);
+    for (int g = 0; g < ss.n; g++) wdpm_destroy(ss.sv[g]);
     free(dem);
     free(water);
     return 0;
