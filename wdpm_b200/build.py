@@ -60,7 +60,7 @@ def build_host(force: bool = False) -> Path | None:
         return None
     if force or _stale(HOST_BIN, [src, ROOT / "include" / "wdpm_b200.h", LIB]):
         cmd = ["/usr/bin/gcc", "-O2", "-std=c11", "-fopenmp", "-Wall", "-Wextra", "-I", str(ROOT / "include"), str(src), "-o", str(HOST_BIN),
-               "-L", str(PKG), "-lwdpm_b200", "-Wl,-rpath,$ORIGIN/..", "-lm"]
+               "-L", str(PKG), "-lwdpm_b200", "-Wl,-rpath,$ORIGIN/..", "-lm", "-lpthread"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("host build failed:\n" + res.stdout + res.stderr)

@@ -24,6 +24,7 @@
 #define _POSIX_C_SOURCE 200809L
 #include <ctype.h>
 #include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -498,6 +499,44 @@ static void set_run_block(solver_set *ss, int iters, wdpm_block_result *out)
     }
 }
 
+/* Scratch (checkpoint) files are written by a background thread while the GPUs run the next block
+ * (the reference writes them inline, WDPMCL.c:1290-1372). The thread owns its own copy of the grid. */
+typedef struct {
+    pthread_t thread;
+    int running;
+    char path[512];
+    asc_header hdr;
+    double *grid;
+} scratch_writer;
+
+static void *scratch_main(void *arg)
+{
+    scratch_writer *sw = arg;
+    write_grid(sw->path, &sw->hdr, sw->grid);
+    return NULL;
+}
+
+static void scratch_join(scratch_writer *sw)
+{
+    if (sw->running) {
+        pthread_join(sw->thread, NULL);
+        sw->running = 0;
+    }
+}
+
+/* hands `grid` (n values) to the writer: copied, so the caller may overwrite it at once */
+static void scratch_start(scratch_writer *sw, const char *path, const asc_header *h, const double *grid, size_t n)
+{
+    scratch_join(sw);
+    if (!sw->grid) sw->grid = malloc(n * sizeof *sw->grid);
+    if (!sw->grid) { write_grid(path, h, grid); return; }
+    memcpy(sw->grid, grid, n * sizeof *grid);
+    snprintf(sw->path, sizeof sw->path, "%s", path);
+    sw->hdr = *h;
+    if (pthread_create(&sw->thread, NULL, scratch_main, sw) == 0) sw->running = 1;
+    else write_grid(path, h, grid);
+}
+
 /* what the scratch file and the Add output hold: water with NODATA cells marked (WDPMCL.c:1336-1344, :1386-1392) */
 static void mark_nodata(double *w, const double *dem, size_t n, double nodata)
 {
@@ -691,6 +730,7 @@ int main(int argc, char **argv)
     struct timeval t0;
     gettimeofday(&t0, NULL);
     int k = 0, done = 0;
+    static scratch_writer scratch;
     while (!done) {
         const double old_drain = total_drain;
         wdpm_block_result r;
@@ -709,9 +749,11 @@ int main(int argc, char **argv)
         if (!done && !is_null_name(a.scratch)) {
             set_download(&ss, water, cols);
             if (is_add) mark_nodata(water, dem, n, nodata);
-            write_grid(a.scratch, &hdr, water);
+            scratch_start(&scratch, a.scratch, &hdr, water, n);
         }
     }
+
+    scratch_join(&scratch);
 
     /* final grid and statistics (WDPMCL.c:1379-1467) */
     set_download(&ss, water, cols);
