@@ -5,8 +5,8 @@
 // (i, j) - the reference's bigdem[i][j] / bigwater[i][j], i in [0,R+1],
 // j in [0,C+1] (src/WDPMCL.c:795-807) - lives at
 //     (i + kPadTop) * pitch + (j + kPadLeft).
-// Elevations are stored MASKED (relax.cuh): a cell with dem <= nodata holds +inf.
-// Everything outside the (R+2)x(C+2) padded grid is margin: dem = +inf,
+// Elevations are stored MASKED (relax.cuh): a cell with dem <= nodata holds the sentinel S.
+// Everything outside the (R+2)x(C+2) padded grid is margin: dem = S,
 // water = 0. A margin cell can never become a centre (dry) nor receive water
 // (invalid neighbour), so kernels may compute on margins freely; this replaces
 // the reference's row/col range guard (src/runoff.cl:145).
@@ -43,8 +43,8 @@ __global__ void k_fill(T* __restrict__ a, long long n, T v) {
         a[i] = v;
 }
 
-// Mask the freshly uploaded DEM in place: dem <= nodata -> +inf (relax.cuh). Runs over the whole
-// device array; margins already hold +inf, which the mask leaves alone.
+// Mask the freshly uploaded DEM in place: dem <= nodata -> S (relax.cuh). Runs over the whole
+// device array; margins already hold S, which the mask leaves alone.
 template <typename T>
 __global__ void k_mask_dem(T* __restrict__ d, long long n, T nodata) {
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
@@ -52,7 +52,7 @@ __global__ void k_mask_dem(T* __restrict__ d, long long n, T nodata) {
 }
 
 // Add-module initial condition, valid cells only (src/WDPMCL.c:778-792). Every cell that is not a
-// valid DEM cell holds +inf elevation, so the whole device array (halo rows of a stripe included)
+// valid DEM cell holds the sentinel elevation, so the whole device array (halo rows of a stripe included)
 // can be swept.
 template <typename T>
 __global__ void k_apply_add(T* __restrict__ w, const T* __restrict__ d, long long n, T depth, T depth_rof) {
@@ -410,7 +410,26 @@ constexpr size_t fused_smem_bytes() {
     return (size_t)2 * CFG::NRING * CFG::W * sizeof(T) + CFG::NSTAGE * sizeof(uint64_t) + 16;
 }
 
-template <typename T, int MODULE, typename CFG, int NTHREADS, int MINB>
+// OPT bit 0 (fp64 Add only; in fp32 the predicated-add form measured faster): cap-free, sign-gated neighbour step (relax.cuh, push_add_fast) - 12 instead
+// of 15 instructions per neighbour, 7 instead of 9 of them on the FP64 pipe.
+constexpr int kOptAddFast = 1;
+
+#ifdef WDPM_TIMELINE
+// Developer probe (never compiled into the product library): per-warp clock64 stamps of one CTA.
+constexpr int kTlSteps = 8, kTlWarps = 32, kTlPoints = 10;
+__device__ long long g_timeline[kTlSteps * kTlWarps * kTlPoints];
+__device__ int g_timeline_cta = 300, g_timeline_step0 = 100;
+#define WDPM_TL(point)                                                                                   \
+    do {                                                                                                 \
+        if ((int)blockIdx.x == g_timeline_cta && (threadIdx.x & 31) == 0 && s >= g_timeline_step0 &&       \
+            s < g_timeline_step0 + kTlSteps)                                                             \
+            g_timeline[((s - g_timeline_step0) * kTlWarps + (threadIdx.x >> 5)) * kTlPoints + (point)] = clock64(); \
+    } while (0)
+#else
+#define WDPM_TL(point) do { } while (0)
+#endif
+
+template <typename T, int MODULE, typename CFG, int NTHREADS, int MINB, int OPT = 0>
 __global__ void __launch_bounds__(NTHREADS + 32, MINB)
 k_fused(const FusedParams<T> p) {
     constexpr int W = CFG::W, NT = CFG::NT, NPH = CFG::NPH, NRING = CFG::NRING, NSTAGE = CFG::NSTAGE, PF = CFG::PF;
@@ -492,6 +511,7 @@ k_fused(const FusedParams<T> p) {
         if (lead)
             for (int s = 0; s < PF && s < tile.n_steps; s++) issue_loads(s);
         for (int s = 0; s < tile.n_steps; s++) {
+            WDPM_TL(0);
             if (lead) {
                 if (s > 0) {
                     issue_stores(s - 1);
@@ -502,11 +522,13 @@ k_fused(const FusedParams<T> p) {
                 if (s + PF < tile.n_steps) issue_loads(s + PF);
             }
             __syncwarp();
+            WDPM_TL(1);
             if (!GROUPED) {
                 __syncthreads();
                 __syncthreads();
             }
             __syncthreads();
+            WDPM_TL(8);
         }
         if (lead) {
             issue_stores(tile.n_steps - 1);
@@ -534,20 +556,21 @@ k_fused(const FusedParams<T> p) {
         it_mrel[k] = t - ph * CFG::LAG;
     }
 
-    for (int s = 0; s < tile.n_steps; s++) {
-        if (step_has_loads(s)) mbar_wait(&bars[s % NSTAGE], (uint32_t)((s / NSTAGE) & 1));
+    constexpr bool ADD_FAST = (OPT & kOptAddFast) && MODULE == kAdd && sizeof(T) == 8;
 
-        // Per tile: the three ring rows it spans this step, and a register window that slides one
-        // column per colour sub-pass. wt = 3x3 water (rows x cols jb-1+cofs .. jb+1+cofs), dd = the
-        // 3x5 elevations under all three positions. Between sub-passes only the column that leaves
-        // the window is written to shared memory (the left-hand tile needs it next) and only the
-        // column that enters is read (the right-hand tile has just published it); after the third
-        // sub-pass the whole window is written back.
-        bool run[IPT], slow[IPT], dirty[IPT];
-        int row0[IPT];
-        T* wrow[IPT][3];
-        T wt[IPT][3][3], dd[IPT][3][5];
-        constexpr int DOFF = NRING * W;  // ring_d = ring_w + DOFF
+    // Per tile: the three ring rows it spans this step, and a register window that slides one
+    // column per colour sub-pass. wt = 3x3 water (rows x cols jb-1+cofs .. jb+1+cofs), dd = the
+    // 3x5 elevations under all three positions. Between sub-passes only the column that leaves
+    // the window is written to shared memory (the left-hand tile needs it next) and only the
+    // column that enters is read (the right-hand tile has just published it); after the third
+    // sub-pass the whole window is written back.
+    bool run[IPT], slow[IPT], dirty[IPT];
+    int row0[IPT];
+    T* wrow[IPT][3];
+    T wt[IPT][3][3], dd[IPT][3][5];
+    constexpr int DOFF = NRING * W;  // ring_d = ring_w + DOFF
+
+    auto prepare = [&](int s) {  // where step s's tiles live, and their elevation windows
 #pragma unroll
         for (int k = 0; k < IPT; k++) {
             const int m = tile.m_lo + NT * s + it_mrel[k];
@@ -557,7 +580,6 @@ k_fused(const FusedParams<T> p) {
             int s1 = s0 + 1; if (s1 == NRING) s1 = 0;
             int s2 = s1 + 1; if (s2 == NRING) s2 = 0;
             wrow[k][0] = ring_w + s0 * W; wrow[k][1] = ring_w + s1 * W; wrow[k][2] = ring_w + s2 * W;
-            dirty[k] = false;
             slow[k] = false;
             if (MODULE == kDrain) {  // tiles that can touch the outlet take the shared-memory path
                 const int c0 = tile.x0 + it_col[k] - 1;
@@ -569,6 +591,22 @@ k_fused(const FusedParams<T> p) {
                 for (int r = 0; r < 3; r++) {
 #pragma unroll
                     for (int cc = 0; cc < 5; cc++) dd[k][r][cc] = wrow[k][r][DOFF + jl + cc];
+                }
+            }
+        }
+    };
+    for (int s = 0; s < tile.n_steps; s++) {
+        WDPM_TL(0);
+        if (step_has_loads(s)) mbar_wait(&bars[s % NSTAGE], (uint32_t)((s / NSTAGE) & 1));
+        WDPM_TL(1);
+        prepare(s);
+#pragma unroll
+        for (int k = 0; k < IPT; k++) {
+            dirty[k] = false;
+            if (run[k] && !slow[k]) {
+                const int jl = it_col[k] - 1;
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
 #pragma unroll
                     for (int cc = 0; cc < 3; cc++) wt[k][r][cc] = wrow[k][r][jl + cc];
                 }
@@ -579,9 +617,8 @@ k_fused(const FusedParams<T> p) {
             constexpr int COFS = decltype(cofs_tag)::value;
 #pragma unroll
             for (int k = 0; k < IPT; k++) {
-                if (!run[k]) continue;
                 const int j = it_col[k] + COFS;  // centre column inside the window
-                if (MODULE == kDrain && slow[k]) {
+                if (MODULE == kDrain && run[k] && slow[k]) {
                     const int crow = row0[k] + 1, ccol = tile.x0 + j;
                     const int orow = p.ds.drainrow - crow, ocol = p.ds.draincol - ccol;
                     T* w0 = wrow[k][0]; T* w1 = wrow[k][1]; T* w2 = wrow[k][2];
@@ -603,7 +640,7 @@ k_fused(const FusedParams<T> p) {
                     }
                     continue;
                 }
-                if (COFS > 0) {  // slide: drop the published left column, read the entering right column
+                if (COFS > 0 && run[k]) {  // slide: drop the published left column, read the entering right column
 #pragma unroll
                     for (int r = 0; r < 3; r++) {
                         wt[k][r][0] = wt[k][r][1];
@@ -611,9 +648,10 @@ k_fused(const FusedParams<T> p) {
                         wt[k][r][2] = wrow[k][r][j + 1];
                     }
                 }
-                const bool active = (wt[k][1][1] > T(0)) && is_valid_elevation(dd[k][1][COFS + 1]);
+                const bool active = run[k] && (wt[k][1][1] > T(0)) && is_valid_elevation(dd[k][1][COFS + 1]);
                 if (active) {
-                    relax_window<T, MODULE, COFS>(wt[k], dd[k]);
+                    if (ADD_FAST) relax_window_add_fast<T, COFS>(wt[k], dd[k]);
+                    else relax_window<T, MODULE, COFS>(wt[k], dd[k]);
                     dirty[k] = true;
                 }
                 if (dirty[k]) {
@@ -635,13 +673,20 @@ k_fused(const FusedParams<T> p) {
             if (GROUPED) asm volatile("bar.sync %0, %1;" ::"r"(1 + tid / CFG::NCP), "n"(CFG::NCP) : "memory");
             else __syncthreads();
         };
+        WDPM_TL(2);
         substep(std::integral_constant<int, 0>{});
+        WDPM_TL(3);
         group_barrier();
+        WDPM_TL(4);
         substep(std::integral_constant<int, 1>{});
+        WDPM_TL(5);
         group_barrier();
+        WDPM_TL(6);
         substep(std::integral_constant<int, 2>{});
         fence_proxy_async();  // make this step's smem writes visible to the bulk-store engine
+        WDPM_TL(7);
         __syncthreads();
+        WDPM_TL(8);
 
     }
 }
@@ -679,7 +724,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 k_resident(const ResidentParams<T> p) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int SR = p.TR + kResHaloTop + kResHaloBottom, SC = p.TC + kResHaloLeft + kResHaloRight;
     T* sw = reinterpret_cast<T*>(smem_raw);  // [SR][SC] water
     T* sd = sw + SR * SC;                    // [SR][SC] masked elevations
@@ -732,7 +777,7 @@ k_resident(const ResidentParams<T> p) {
                         continue;
                     }
                 }
-                relax_tile<T, MODULE>(w0, w1, w2, d0, d1, d2, j);
+                relax_tile<T, MODULE, true>(w0, w1, w2, d0, d1, d2, j);
             }
             __syncthreads();
         }

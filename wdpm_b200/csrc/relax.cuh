@@ -7,12 +7,13 @@
 // with the centre guard of src/runoff.cl:145 / :160 / :177-179.
 //
 // MASKED ELEVATIONS. The solver stores the DEM with every invalid cell
-// (dem <= nodata, i.e. NODATA cells, the halo ring and the device margins)
-// replaced by +infinity. A neighbour at +inf has surface sn = +inf, so the
-// height difference h = sc - sn is -inf and the `h > 0` test fails exactly
-// where the reference's `bigdem[n] > missingvalue` guard (runoff.cl:33) would
+// (dem <= nodata, i.e. NODATA cells, the halo ring and the device margins; also
+// NaN, infinite or absurdly large inputs) replaced by a sentinel S = the largest
+// power of two of the format. A neighbour at S has surface sn = S, so the height
+// difference h = sc - sn is -S (finite, hugely negative) and the `h > 0` test fails
+// exactly where the reference's `bigdem[n] > missingvalue` guard (runoff.cl:33) would
 // have skipped the neighbour: the validity compare and its branch disappear
-// from the inner loop. A centre is valid iff its elevation is finite.
+// from the inner loop. A centre is valid iff its elevation is below S.
 //
 // The step is written branch-free (selects / predicated adds) against
 // register-resident values: the eight neighbour steps of a tile form one
@@ -46,19 +47,22 @@ namespace wdpm {
 
 enum : int { kAdd = 0, kSubtract = 1, kDrain = 2 };
 
+// What the solver stores for an invalid cell: the largest power of two of the format (2^1023, 2^127).
+// Finite on purpose: surfaces and height differences against it stay finite (-2^1023 etc.), so a
+// closed gate can be expressed as a multiplication by zero (push_add_fast) without producing NaN.
 template <typename T>
 WDPM_HD T invalid_elevation() {
 #ifdef __CUDA_ARCH__
-    return sizeof(T) == 8 ? (T)__longlong_as_double(0x7ff0000000000000LL) : (T)__int_as_float(0x7f800000);
+    return sizeof(T) == 8 ? (T)__longlong_as_double(0x7fe0000000000000LL) : (T)__int_as_float(0x7f000000);
 #else
-    return std::numeric_limits<T>::infinity();
+    return sizeof(T) == 8 ? (T)8.98846567431158e307 : (T)1.7014118346046923e38f;
 #endif
 }
 template <typename T>
 WDPM_HD bool is_valid_elevation(T d) { return d < invalid_elevation<T>(); }
 // what the upload path stores for a raw elevation
 template <typename T>
-WDPM_HD T mask_elevation(T d, T nodata) { return (d > nodata) ? d : invalid_elevation<T>(); }
+WDPM_HD T mask_elevation(T d, T nodata) { return (d > nodata && d < invalid_elevation<T>()) ? d : invalid_elevation<T>(); }
 
 // A 3x3 tile held in registers. Neighbour order: row offset outer, column
 // offset inner (src/runoff.cl:28-30): 0 1 2 / 3 c 4 / 5 6 7.
@@ -142,6 +146,76 @@ WDPM_HD void push(T dc, T& wc, T dn, T& wn) {
     move_if(pos, wc, wn, flow);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Add module: the same step with fewer instructions on the FP64 pipe (the pipe that bounds the
+// fused kernel while the tile chains run). Two rewrites, both value-preserving:
+//
+//  (1) NO CAP. In runoffadd, mini(flow, wc) (runoff.cl:46) never changes flow. For dc > sn,
+//      flow = wc/8 <= wc. For dc <= sn: sc = fl(dc + wc) is the floating-point number nearest to
+//      dc + wc, and dc itself is a floating-point number at distance wc from it, so
+//      |sc - (dc + wc)| <= wc, i.e. sc <= dc + 2 wc. With sn >= dc, sc - sn <= 2 wc, and rounding
+//      is monotonic, so h = fl(sc - sn) <= 2 wc and flow = fl(h/8) <= fl(wc/4) <= wc. (Holds in
+//      any binary format with round-to-nearest, for every wc >= 0; tests/test_relax_rewrites.py
+//      hammers it with adversarial chains.) The four-term flow of runoffsubtract / runoffdrain has
+//      no such bound (it can exceed a tiny wc next to a deep neighbour), so those keep the cap.
+//
+//  (2) SIGN GATE. With x = (dc > sn) ? wc : h the reference's `if (h > 0)` is equivalent to "x is
+//      not negative": dc > sn implies sc = fl(dc + wc) >= dc > sn (wc >= 0), hence h > 0; and when
+//      dc <= sn, x = h. So the gate is read off x's sign bit with an integer compare (ALU pipe)
+//      instead of a DSETP. The one value the two tests disagree on is h == +0: the sign gate lets
+//      flow = +0 through, which changes nothing (wc - 0 = wc, wn + 0 = wn) unless wn is -0.0,
+//      which then becomes +0.0. Water is never -0.0 unless a water FILE holds a negative zero and
+//      the zero threshold is 0 (and Add rewrites every valid cell first, WDPMCL.c:778-792), so
+//      the Add module cannot observe it.
+template <typename T>
+WDPM_HD bool sign_clear(T x) {
+#ifdef __CUDA_ARCH__
+    if (sizeof(T) == 8) return __double2hiint((double)x) >= 0;
+    return __float_as_int((float)x) >= 0;
+#else
+    return !std::signbit(x);
+#endif
+}
+
+template <typename T>
+WDPM_HD void push_add_fast(T dc, T& wc, T dn, T& wn) {
+    const T sn = dn + wn;
+    const T sc = dc + wc;
+    const T h = sc - sn;
+    const bool q = dc > sn;
+    const T x = q ? wc : h;
+#ifdef __CUDA_ARCH__
+    if (sizeof(T) == 8) {
+        // Gate folded into the scaling: x * (open ? 0.125 : +0.0). A closed gate has x = h < 0 and
+        // FINITE (invalid elevations are a huge finite number, not infinity), so the product is
+        // exactly -0.0, the additive identity. open = "h is not negative" (dc > sn implies h > 0,
+        // see above), read off h's sign bit; only the high word of the factor is selected.
+        int mhi;
+        asm("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %1, 0;\n\tselp.b32 %0, 0x3fc00000, 0, p;\n\t}" : "=r"(mhi) : "r"(__double2hiint((double)h)));
+        const T give = (T)((double)x * __hiloint2double(mhi, 0));
+        wc = wc - give;
+        wn = wn + give;
+        return;
+    }
+#endif
+    move_if(sign_clear(x), wc, wn, x * T(0.125));
+}
+
+template <typename T, int COFS>
+WDPM_HD void relax_window_add_fast(T (&w)[3][3], const T (&d)[3][5]) {
+    const T dc = d[1][COFS + 1];
+    T wc = w[1][1];
+    push_add_fast<T>(dc, wc, d[0][COFS + 0], w[0][0]);
+    push_add_fast<T>(dc, wc, d[0][COFS + 1], w[0][1]);
+    push_add_fast<T>(dc, wc, d[0][COFS + 2], w[0][2]);
+    push_add_fast<T>(dc, wc, d[1][COFS + 0], w[1][0]);
+    push_add_fast<T>(dc, wc, d[1][COFS + 2], w[1][2]);
+    push_add_fast<T>(dc, wc, d[2][COFS + 0], w[2][0]);
+    push_add_fast<T>(dc, wc, d[2][COFS + 1], w[2][1]);
+    push_add_fast<T>(dc, wc, d[2][COFS + 2], w[2][2]);
+    w[1][1] = wc;
+}
+
 // The same eight steps on a register window that slides one column per colour sub-pass:
 // w holds the tile's 3x3 water (rows x cols), d the elevations of the 3x5 cells the tile
 // covers over the three sub-passes; COFS (0,1,2) selects which three elevation columns apply.
@@ -160,22 +234,27 @@ WDPM_HD void relax_window(T (&w)[3][3], const T (&d)[3][5]) {
     w[1][1] = wc;
 }
 
-// The eight neighbour steps of one tile (only meaningful when t.active).
-template <typename T, int MODULE>
+// The eight neighbour steps of one tile (only meaningful when t.active). FAST selects the fp64 Add
+// rewrite (push_add_fast; in fp32 the predicated form of move_if measured faster); the plain form is what the colour kernel - the
+// second, independent CUDA path - and the CPU checks run.
+template <typename T, int MODULE, bool FAST = false>
 WDPM_HD void tile_relax(Tile<T>& t) {
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-    for (int n = 0; n < 8; n++) push<T, MODULE>(t.dc, t.wc, t.dn[n], t.wn[n]);
+    for (int n = 0; n < 8; n++) {
+        if (FAST && MODULE == kAdd && sizeof(T) == 8) push_add_fast<T>(t.dc, t.wc, t.dn[n], t.wn[n]);
+        else push<T, MODULE>(t.dc, t.wc, t.dn[n], t.wn[n]);
+    }
 }
 
 // Convenience: load, relax if active, store. Returns whether work was done.
-template <typename T, int MODULE>
+template <typename T, int MODULE, bool FAST = false>
 WDPM_HD bool relax_tile(T* w0, T* w1, T* w2, const T* d0, const T* d1, const T* d2, int j) {
     Tile<T> t;
     tile_load(t, w0, w1, w2, d0, d1, d2, j);
     if (!t.active) return false;
-    tile_relax<T, MODULE>(t);
+    tile_relax<T, MODULE, FAST>(t);
     tile_store(t, w0, w1, w2, j);
     return true;
 }

@@ -17,7 +17,7 @@ using namespace wdpm;
 
 namespace {
 
-constexpr int kDefaultVariantF64 = 10;  // 384-column window, two row triples per phase, 24 compute warps
+constexpr int kDefaultVariantF64 = 11;  // 384-column window, two row triples per phase, 24 compute warps, Add fast step
 constexpr int kDefaultVariantF32 = 7;   // 512-column window, two CTAs of 16 compute warps per SM
 constexpr int kDefaultVariantF64Drain = 1;  // Drain's relax step needs more registers than 24 warps leave: 16 warps, 512 columns
 // Grids of a few hundred thousand cells (the reference's basin5 is 482 x 471) cannot fill 148 SMs
@@ -58,33 +58,34 @@ struct FusedVariant {
     cudaError_t (*prepare)();
 };
 
-template <typename T, int MODULE, typename CFG, int NTHREADS, int MINB>
+template <typename T, int MODULE, typename CFG, int NTHREADS, int MINB, int OPT>
 cudaError_t launch_fused(const FusedParams<T>& p, int grid, cudaStream_t st) {
-    k_fused<T, MODULE, CFG, NTHREADS, MINB><<<grid, NTHREADS + 32, fused_smem_bytes<CFG, T>(), st>>>(p);  // +1 data-movement warp
+    k_fused<T, MODULE, CFG, NTHREADS, MINB, OPT><<<grid, NTHREADS + 32, fused_smem_bytes<CFG, T>(), st>>>(p);  // +1 data-movement warp
     return cudaGetLastError();
 }
 
-template <typename T, typename CFG, int NTHREADS, int MINB>
+template <typename T, typename CFG, int NTHREADS, int MINB, int OPT>
 cudaError_t prepare_fused() {
     const int smem = (int)fused_smem_bytes<CFG, T>();
     cudaError_t e;
-    e = cudaFuncSetAttribute(k_fused<T, kAdd, CFG, NTHREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = cudaFuncSetAttribute(k_fused<T, kAdd, CFG, NTHREADS, MINB, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_fused<T, kSubtract, CFG, NTHREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = cudaFuncSetAttribute(k_fused<T, kSubtract, CFG, NTHREADS, MINB, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_fused<T, kDrain, CFG, NTHREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    return cudaFuncSetAttribute(k_fused<T, kDrain, CFG, NTHREADS, MINB, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
-template <typename T, typename CFG, int NTHREADS, int MINB>
+// OPT: kernels.cuh (kOptAddFast only affects the Add instantiation)
+template <typename T, typename CFG, int NTHREADS, int MINB, int OPT = 0>
 FusedVariant<T> make_variant() {
     FusedVariant<T> v;
     v.W = CFG::W; v.TWV = CFG::TWV; v.HL = CFG::HL; v.K = CFG::K; v.NT = CFG::NT; v.PF = CFG::PF;
     v.nthreads = NTHREADS; v.minb = MINB;
     v.smem = fused_smem_bytes<CFG, T>();
-    v.launch[kAdd] = launch_fused<T, kAdd, CFG, NTHREADS, MINB>;
-    v.launch[kSubtract] = launch_fused<T, kSubtract, CFG, NTHREADS, MINB>;
-    v.launch[kDrain] = launch_fused<T, kDrain, CFG, NTHREADS, MINB>;
-    v.prepare = prepare_fused<T, CFG, NTHREADS, MINB>;
+    v.launch[kAdd] = launch_fused<T, kAdd, CFG, NTHREADS, MINB, OPT>;
+    v.launch[kSubtract] = launch_fused<T, kSubtract, CFG, NTHREADS, MINB, OPT>;
+    v.launch[kDrain] = launch_fused<T, kDrain, CFG, NTHREADS, MINB, OPT>;
+    v.prepare = prepare_fused<T, CFG, NTHREADS, MINB, OPT>;
     return v;
 }
 
@@ -107,6 +108,8 @@ const std::vector<FusedVariant<double>>& fused_variants<double>() {
         make_variant<double, MwCfg<384, 2, 1, 1>, 384, 1>(),   // 8: two triples per phase, two tiles per thread (exact fit)
         make_variant<double, MwCfg<384, 2, 1, 1>, 256, 1>(),   // 9: two triples per phase, three tiles per thread
         make_variant<double, MwCfg<384, 2, 1, 1>, 768, 1>(),   // 10: two triples per phase, 24 warps, one tile per thread
+        make_variant<double, MwCfg<384, 2, 1, 1>, 768, 1, kOptAddFast>(),  // 11: as 10, Add with the sign gate and cap-free chains
+        make_variant<double, MwCfg<64, 1, 1, 1>, 128, 1, kOptAddFast>(),   // 12: test window with the Add fast path
     };
     return v;
 }
@@ -728,7 +731,7 @@ int wdpm_upload(wdpm_solver* s, const void* dem, const void* water) {
     CUDA_TRY(cudaSetDevice(s->device));
     int rc = upload_grid(s, s->dem, dem);
     if (rc) return rc;
-    {   // store elevations masked: dem <= nodata -> +inf (relax.cuh)
+    {   // store elevations masked: dem <= nodata -> sentinel (relax.cuh)
         const long long n = s->g.cells_dev();
         const int grid = grid_for(n, 256, s->sm_count);
         if (s->dtype == WDPM_F64) k_mask_dem<double><<<grid, 256, 0, s->stream>>>(static_cast<double*>(s->dem), n, s->cfg.nodata);
@@ -1080,5 +1083,19 @@ int wdpm_stripe_phase(wdpm_solver* s, int32_t phase) {
     if (phase == 1) return halo_push(s);
     return fail(WDPM_E_ARG, "phase must be 0 or 1");
 }
+
+#ifdef WDPM_TIMELINE
+// Developer probe (scripts/timeline.py builds a separate library with -DWDPM_TIMELINE).
+int wdpm_debug_timeline(int32_t cta, int32_t step0, long long* out, int32_t n) {
+    if (out) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(cudaMemcpyFromSymbol(out, g_timeline, sizeof(long long) * (size_t)n));
+        return WDPM_OK;
+    }
+    CUDA_TRY(cudaMemcpyToSymbol(g_timeline_cta, &cta, sizeof(int)));
+    CUDA_TRY(cudaMemcpyToSymbol(g_timeline_step0, &step0, sizeof(int)));
+    return WDPM_OK;
+}
+#endif
 
 }  // extern "C"

@@ -64,7 +64,9 @@ _lib = None
 
 
 def library_path() -> Path:
-    return _PKG / "libwdpm_b200.so"
+    # WDPM_B200_LIB: developer hook (scripts/timeline.py loads an instrumented build of the same sources)
+    import os
+    return Path(os.environ.get("WDPM_B200_LIB") or (_PKG / "libwdpm_b200.so"))
 
 
 def load_library() -> C.CDLL:
