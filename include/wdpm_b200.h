@@ -126,7 +126,16 @@ int wdpm_apply_subtract(wdpm_solver *s, double depth);
  * Returns WDPM_E_STATE if no cell has dem > 0. */
 int wdpm_find_outlet(wdpm_solver *s, int32_t *drainrow, int32_t *draincol, double *min_elevation);
 int wdpm_set_outlet(wdpm_solver *s, int32_t drainrow, int32_t draincol);
-/* totaldrain accumulator (src/WDPMCL.c:1029, :1136) */
+/* Extension (BASELINE configs[4], "many drain outlets"): a SET of outlet cells, in padded
+ * coordinates of the whole DEM. Each outlet follows src/runoff.cl:104-111 - never a centre; a
+ * neighbouring centre empties itself and the outlet into that outlet's total. One outlet is the
+ * reference. Every outlet has its own accumulator; the reported total is their sum in outlet order
+ * (solver precision). Replaces any earlier set. Drain solvers only. */
+#define WDPM_MAX_OUTLETS 1024
+int wdpm_set_outlets(wdpm_solver *s, int32_t n, const int32_t *rows, const int32_t *cols);
+int wdpm_get_outlet_drains(wdpm_solver *s, double *values, int32_t n);
+/* totaldrain accumulator (src/WDPMCL.c:1029, :1136); with an outlet set, set writes the first
+ * outlet's total and zeroes the others, get returns the sum */
 int wdpm_set_total_drain(wdpm_solver *s, double value);
 int wdpm_get_total_drain(wdpm_solver *s, double *value);
 /* water depth at one cell (for totaldrain = max(bigwater[outlet],0), src/WDPMCL.c:1029) */

@@ -96,6 +96,21 @@ class Oracle:
            _ptr(td), C.byref(md), C.byref(ms))
         return md.value, ms.value, float(td[0])
 
+    def iterate_outlets(self, w: np.ndarray, d: np.ndarray, nodata: float, n_iters: int, outlets, totals=None):
+        """Drain with a SET of outlets (extension; one outlet = the reference). In place on w; returns the
+        per-outlet totals (dtype of w)."""
+        sfx, ct = _sfx(w.dtype)
+        R, Cc = w.shape[0] - 2, w.shape[1] - 2
+        rows = np.ascontiguousarray([o[0] for o in outlets], dtype=np.int32)
+        cols = np.ascontiguousarray([o[1] for o in outlets], dtype=np.int32)
+        td = np.zeros(len(outlets), dtype=w.dtype) if totals is None else np.ascontiguousarray(totals, dtype=w.dtype).copy()
+        fn = getattr(self.lib, "wdpm_oracle_iterate_outlets" + sfx)
+        fn.restype = C.c_int
+        rc = fn(_ptr(w), _ptr(d), C.c_int(R), C.c_int(Cc), ct(nodata), C.c_int(n_iters), C.c_int(len(outlets)),
+                _ptr(rows), _ptr(cols), _ptr(td))
+        assert rc == 0
+        return td
+
     def find_outlet(self, d):
         sfx, _ = _sfx(d.dtype)
         R, Cc = d.shape[0] - 2, d.shape[1] - 2

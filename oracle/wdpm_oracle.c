@@ -4,6 +4,7 @@
  */
 #include <math.h>
 #include <stddef.h>
+#include <stdlib.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif

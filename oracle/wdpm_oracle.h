@@ -30,7 +30,10 @@ extern "C" {
                                 int module, int schedule, REAL thres, int n_iters, int drainrow, \
                                 int draincol, REAL *totaldrain, double *max_diff,                \
                                 double *masked_sum);                                             \
-    int wdpm_oracle_find_outlet##SFX(const REAL *d, int R, int C, int *drainrow, int *draincol);
+    int wdpm_oracle_find_outlet##SFX(const REAL *d, int R, int C, int *drainrow, int *draincol);     \
+    int wdpm_oracle_iterate_outlets##SFX(REAL *w, const REAL *d, int R, int C, REAL nodata,          \
+                                         int n_iters, int n_outlets, const int *rows,               \
+                                         const int *cols, REAL *totals);
 
 WDPM_ORACLE_DECL(double, _f64)
 WDPM_ORACLE_DECL(float, _f32)

@@ -242,6 +242,67 @@ void FN(wdpm_oracle_iterate)(REAL *w, const REAL *d, int R, int C, REAL nodata,
     }
 }
 
+/* EXTENSION (not in the reference, which has exactly one outlet): Drain with a SET of outlets,
+ * the semantics wdpm_set_outlets() of the product defines and BASELINE configs[4] asks for. Every
+ * outlet behaves as runoff.cl:104-111 prescribes for the one outlet - it is never a centre
+ * (runoff.cl:179), and a centre next to it adds w[outlet] + w[centre] to THAT outlet's total and
+ * zeroes both, before any height test. `oid` maps a padded cell to its outlet index or -1. With one
+ * outlet this is relax_drain_cl. OpenCL-branch arithmetic only. */
+static void FN(relax_drain_set)(REAL *w, const REAL *d, int pitch, int ci, int cj, REAL nodata,
+                                const int *oid, REAL *totals)
+{
+    for (int i = ci - 1; i <= ci + 1; i++) {
+        for (int j = cj - 1; j <= cj + 1; j++) {
+            if ((i != ci || j != cj) && d[IDX(i, j)] > nodata) {
+                REAL centre_elev = d[IDX(ci, cj)] + w[IDX(ci, cj)];
+                REAL cell_elev = d[IDX(i, j)] + w[IDX(i, j)];
+                const int k = oid[IDX(i, j)];
+                if (k >= 0) {
+                    totals[k] = totals[k] + w[IDX(i, j)] + w[IDX(ci, cj)];
+                    w[IDX(i, j)] = (REAL)0.0;
+                    w[IDX(ci, cj)] = (REAL)0.0;
+                } else {
+                    REAL h = centre_elev - cell_elev;
+                    if (h > 0) {
+                        REAL flow;
+                        if (d[IDX(ci, cj)] > cell_elev)
+                            flow = w[IDX(ci, cj)] / (REAL)8.0;
+                        else
+                            flow = ((d[IDX(ci, cj)] - d[IDX(i, j)]) +
+                                    (w[IDX(ci, cj)] - w[IDX(i, j)])) / (REAL)8.0;
+                        flow = FN(cl_mini)(FN(cl_maxi)(flow, (REAL)0.0), w[IDX(ci, cj)]);
+                        w[IDX(ci, cj)] = FN(cl_maxi)(w[IDX(ci, cj)] - flow, (REAL)0.0);
+                        w[IDX(i, j)] = w[IDX(i, j)] + flow;
+                    }
+                }
+            }
+        }
+    }
+}
+
+/* n_iters Drain iterations with an outlet set; totals[k] accumulates outlet k's contacts. Serial
+ * inside a sub-pass (an outlet has at most one neighbouring centre per colour, so the order is
+ * immaterial; kept serial for simplicity). Returns -1 on allocation failure. */
+int FN(wdpm_oracle_iterate_outlets)(REAL *w, const REAL *d, int R, int C, REAL nodata, int n_iters,
+                                    int n_outlets, const int *rows, const int *cols, REAL *totals)
+{
+    const int pitch = C + 2;
+    const size_t n = (size_t)(R + 2) * (size_t)(C + 2);
+    int *oid = (int *)malloc(n * sizeof *oid);
+    if (!oid) return -1;
+    for (size_t k = 0; k < n; k++) oid[k] = -1;
+    for (int k = 0; k < n_outlets; k++) oid[IDX(rows[k], cols[k])] = k;
+    for (int it = 0; it < n_iters; it++)
+        for (int oi = 1; oi <= 3; oi++)
+            for (int oj = 1; oj <= 3; oj++)
+                for (int i = oi; i <= R; i += 3)
+                    for (int j = oj; j <= C; j += 3)
+                        if (w[IDX(i, j)] > (REAL)0.0 && d[IDX(i, j)] > nodata && oid[IDX(i, j)] < 0)
+                            FN(relax_drain_set)(w, d, pitch, i, j, nodata, oid, totals);
+    free(oid);
+    return 0;
+}
+
 /* One convergence block (WDPMCL.c:1054-1268): zero-threshold over the whole
  * padded grid (:1055-1065), snapshot (:1069-1073), n_iters iterations, then
  * max |w-old| over valid cells seeded with cell [0][0] (:1239-1254) and the

@@ -2,10 +2,11 @@
 """BASELINE.json configs[4] at the reference's semantics: Drain on a synthetic DEM of --size^2 cells in fp64,
 row stripes over all ranks (one process per GPU), starting from a uniform --water-mm layer.
 
-The reference has exactly one outlet (lowest cell with dem > 0, src/WDPMCL.c:1005-1017); the "many
-outlets" of configs[4] is an extension this repository does not implement.
-Checks the size-independent property a Drain run offers: water left + water drained = water put in,
-to rounding, and that the outlet found by the stripes is the global minimum.
+The reference has exactly one outlet (lowest cell with dem > 0, src/WDPMCL.c:1005-1017): outlet 0 here.
+--outlets K > 1 adds the "many drain outlets" of configs[4] through wdpm_set_outlets (an extension,
+include/wdpm_b200.h): the K-1 lowest cells of the DEM's rim (first/last row and column), ties by
+row-major position. Checks the size-independent property a Drain run offers: water left + water
+drained = water put in, to rounding, and that the outlet found by the stripes is the global minimum.
 
 python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 scripts/large_drain.py --size 65536 --blocks 2
 """
@@ -29,6 +30,7 @@ ap.add_argument("--size", type=int, default=65536)
 ap.add_argument("--blocks", type=int, default=2)
 ap.add_argument("--water-mm", type=float, default=300.0)
 ap.add_argument("--thres-mm", type=float, default=0.0, help="zero-depth threshold; > 0 destroys mass (SURVEY appendix A quirk 6), so the balance check needs 0")
+ap.add_argument("--outlets", type=int, default=64, help="size of the outlet set (1 = the reference's single outlet)")
 ap.add_argument("--out", default="")
 a = ap.parse_args()
 
@@ -41,6 +43,18 @@ t0 = time.time()
 dem = synth.fractal_dem(n, n, seed=n, device=f"cuda:{local}", dtype=torch.float64)
 gmin = float(dem.min().item())
 gpos = int(torch.argmin(dem).item())  # first occurrence in row-major order = the reference's tie rule
+rim = []
+if a.outlets > 1:  # every rank holds the whole DEM here, so every rank picks the same rim cells
+    idx = torch.arange(n, device=dem.device)
+    zeros, last = torch.zeros_like(idx), torch.full_like(idx, n - 1)
+    rr = torch.cat([zeros, last, idx[1:-1], idx[1:-1]])
+    cc = torch.cat([idx, idx, zeros[1:-1], last[1:-1]])
+    ev = dem[rr, cc]
+    key = rr * n + cc
+    order = torch.argsort(key)          # row-major first, then a stable sort by elevation: ties -> first in row-major order
+    ev, key = ev[order], key[order]
+    pick = torch.argsort(ev, stable=True)[: a.outlets + 1]
+    rim = [(int(k) // n + 1, int(k) % n + 1) for k in key[pick].tolist()]  # padded coordinates
 from wdpm_b200.stripes import plan_stripes  # noqa: E402
 st = plan_stripes(n, world)[rank]
 band = dem[st.band_row0:st.band_row0 + st.band_rows].cpu().numpy()
@@ -61,7 +75,8 @@ allc = [None] * world
 dist.all_gather_object(allc, cand)
 best = min((c for c in allc if c is not None), key=lambda c: (c[2], c[0], c[1]))
 assert best[2] == gmin and (best[0] - 1) * n + (best[1] - 1) == gpos, (best, gmin, gpos)
-ds.solver.set_outlet(best[0], best[1])
+outlets = [(best[0], best[1])] + [rc for rc in rim if rc != (best[0], best[1])][: a.outlets - 1]
+ds.solver.set_outlets(outlets)
 owner = st.row0 <= best[0] < st.row0 + st.rows
 w_out = ds.solver.get_cell_water(best[0], best[1]) if owner else 0.0
 ds.solver.set_total_drain(max(w_out, 0.0) if owner else 0.0)  # src/WDPMCL.c:1029
@@ -82,6 +97,7 @@ for b in range(a.blocks):
 if rank == 0:
     info = ds.solver.info()
     summary = {"size": n, "gpus": world, "dtype": "f64", "module": "drain", "outlet": [best[0], best[1]], "min_elevation": best[2],
+               "n_outlets": len(outlets), "outlets_head": outlets[:8],
                "setup_s": t_setup, "device_bytes_per_gpu": info["device_bytes"], "blocks": lines}
     print(json.dumps(summary))
     if a.out:

@@ -100,12 +100,11 @@ void run_cta(const Layout& L, const T* w_in, T* w_out, const T* dem, T nodata, i
                     const int crow = row0 + 1, ccol = tile.x0 + j;
                     const int orow = drainrow - crow, ocol = draincol - ccol;
                     if (orow >= -1 && orow <= 1 && ocol >= -1 && ocol <= 1) {
-                        if (orow == 0 && ocol == 0) continue;
-                        T evo, evc; bool drained;
-                        relax_tile_at_outlet<T>(w0, w1, w2, d0, d1, d2, j, orow, ocol, &evo, &evc, &drained);
-                        if (drained && tile.owns_row(crow) && tile.owns_col(ccol)) {
+                        T evo[8], evc[8]; int pos[8];
+                        const int n = relax_tile_near_outlets<T>(w0, w1, w2, d0, d1, d2, j, 1 << ((orow + 1) * 3 + (ocol + 1)), evo, evc, pos);
+                        if (n && tile.owns_row(crow) && tile.owns_col(ccol)) {
                             Event<T>& e = events[(ph / 3) * 9 + q * 3 + cofs];
-                            e.w_outlet = evo; e.w_centre = evc; e.valid = 1;
+                            e.w_outlet = evo[0]; e.w_centre = evc[0]; e.valid = 1;
                         }
                         continue;
                     }

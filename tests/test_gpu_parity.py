@@ -111,6 +111,75 @@ def test_fused_drain_outlet_on_ownership_boundaries(cuda_lib, oracle):
         assert np.array_equal(a, b) and ta == tb, (orow, ocol)
 
 
+def _outlet_set(D, rng, twv):
+    """Outlets that stress the bookkeeping: neighbours of each other, on strip / chunk borders, on the rim."""
+    R, Cc = D.shape[0] - 2, D.shape[1] - 2
+    want = [(1, 1), (1, 2), (2, 2), (R, Cc), (15, min(twv, Cc)), (15, min(twv + 1, Cc)), (16, min(twv - 1, Cc)), (30, 7), (32, 9), (R // 2, 1)]
+    for _ in range(6):
+        want.append((int(rng.integers(1, R + 1)), int(rng.integers(1, Cc + 1))))
+    out = []
+    for rc in want:
+        if D[rc] > NODATA and rc not in out:
+            out.append(rc)
+    return out
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("kernel,variant", [(1, 0), (2, 1), (2, 2), (2, 3), (3, 0)])
+def test_drain_outlet_set_matches_oracle(cuda_lib, oracle, dt, kernel, variant):
+    """Extension (BASELINE configs[4]): a set of outlets. Water grid and every outlet's total, bit for bit."""
+    from wdpm_b200 import F32, F64, Solver, solver
+    code = F64 if dt == np.float64 else F32
+    twv = solver.fused_variant_info(2, code)["strip_cols"]
+    rng = np.random.default_rng(77)
+    for rows, cols, chunk_rows, n in ((60, 90, 15, 7), (45, 200, 0, 5)):
+        D, W = random_case(rng, rows, cols, dt, nodata_fraction=0.04, wet_fraction=0.9)
+        outlets = _outlet_set(D, rng, twv)
+        assert len(outlets) >= 10
+        a = W.copy()
+        t0 = np.zeros(len(outlets), dtype=dt)
+        t0[0] = dt(0.5)
+        ta = oracle.iterate_outlets(a, D, NODATA, n, outlets, totals=t0)
+        s = Solver(rows, cols, NODATA, 2, dtype=code, kernel=kernel, fused_variant=variant, fused_chunk_rows=chunk_rows if kernel == 2 else 0)
+        s.upload(D[1:-1, 1:-1], W[1:-1, 1:-1])
+        s.set_outlets(outlets)
+        s.set_total_drain(0.5)
+        s.iterate(n)
+        b = ascgrid.pad_grid(s.download_water(), dt(0))
+        tb = s.get_outlet_drains(len(outlets)).astype(dt)
+        total = s.get_total_drain()
+        s.close()
+        assert np.array_equal(a, b), (rows, cols, int((a != b).sum()))
+        assert np.array_equal(ta, tb), (ta, tb)
+        acc = ta[0]
+        for v in ta[1:]:
+            acc = dt(acc + v)
+        assert dt(total) == acc
+
+
+def test_outlet_set_can_be_replaced_and_survives_upload(cuda_lib, oracle):
+    """Marks are taken out when the set changes, and put back after a fresh DEM upload."""
+    from wdpm_b200 import F64, Solver
+    rng = np.random.default_rng(78)
+    D, W = random_case(rng, 40, 50, np.float64, nodata_fraction=0.0, wet_fraction=1.0)
+    first, second = [(5, 5), (6, 6), (20, 30)], [(10, 10), (33, 41)]
+    s = Solver(40, 50, NODATA, 2, dtype=F64, kernel=2, fused_variant=2)
+    s.upload(D[1:-1, 1:-1], W[1:-1, 1:-1])
+    s.set_outlets(first)
+    s.set_outlets(second)          # the cells of `first` must get their elevations back
+    s.upload(D[1:-1, 1:-1], W[1:-1, 1:-1])   # and `second` must be marked again in the new grid
+    s.set_total_drain(0.0)
+    s.iterate(4)
+    b = ascgrid.pad_grid(s.download_water(), 0.0)
+    tb = s.get_outlet_drains(2)
+    r, c, _ = s.find_outlet()      # searches true elevations, then installs the reference's single outlet
+    s.close()
+    a = W.copy()
+    ta = oracle.iterate_outlets(a, D, NODATA, 4, second)
+    assert np.array_equal(a, b) and np.array_equal(ta, tb)
+    assert (r, c) == oracle.find_outlet(D)
+
+
 @pytest.mark.parametrize("dn,dt", [("f64", np.float64), ("f32", np.float32)])
 @pytest.mark.parametrize("mn,mod", MODS)
 @pytest.mark.parametrize("kernel", [1, 2])

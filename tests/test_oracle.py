@@ -162,3 +162,15 @@ def test_drain_report_matches_reference_log(oracle, basin5):
     assert "%10.4f" % rep.water_frac in log         # Final water coverage
     assert "%10.2f" % (rep.mean_water * 1000.0) in log
     assert "%10.2f" % rep.max_depth_mm in log
+
+
+def test_outlet_set_extension_reduces_to_the_reference_for_one_outlet(oracle):
+    """oracle.iterate_outlets (the many-outlets extension) with ONE outlet is runoffdrain."""
+    rng = np.random.default_rng(41)
+    for dt in (np.float64, np.float32):
+        D, W = random_case(rng, 37, 52, dt)
+        outlet = oracle.find_outlet(D)
+        a, b = W.copy(), W.copy()
+        ta = oracle.iterate(a, D, -99999.0, po.DRAIN, 6, outlet=outlet, totaldrain=0.25)
+        tb = oracle.iterate_outlets(b, D, -99999.0, 6, [outlet], totals=[0.25])
+        assert np.array_equal(a, b) and dt(ta) == tb[0]

@@ -207,9 +207,10 @@ __global__ void k_find_outlet_stage2(const OutletCand* __restrict__ partials, in
 }
 
 // ---------------------------------------------------------------------------
-// Drain bookkeeping. totaldrain is one accumulator in the solver's precision
-// (src/runoff.cl:108). An event is the pair of addends of one outlet contact,
-// folded as (totaldrain + w_outlet) + w_centre, in sub-pass order.
+// Drain bookkeeping. Every outlet has its own accumulator in the solver's precision (one outlet:
+// the reference's totaldrain, src/runoff.cl:108). An event is the pair of addends of one outlet
+// contact, folded as (total + w_outlet) + w_centre, in sub-pass order. An outlet is a neighbour of
+// at most one centre per colour sub-pass, so (outlet, sub-pass) identifies a contact.
 // ---------------------------------------------------------------------------
 
 template <typename T>
@@ -222,30 +223,90 @@ struct DrainEvent {
 
 template <typename T>
 struct DrainState {
-    T* totaldrain;          // device scalar
-    DrainEvent<T>* events;  // [2][9*kMaxItersPerLaunch], double-buffered by launch parity
-    int drainrow, draincol; // padded coordinates; (-10,-10) when unset
+    T* totaldrain;          // [n_outlets] device accumulators
+    DrainEvent<T>* events;  // [2][n_outlets][9*kMaxItersPerLaunch], double-buffered by launch parity
+    const int* outlet_rc;   // [n_outlets][2] padded (row, col) of each outlet in this solver's rows
+    int n_outlets;
 };
 
 constexpr int kEventsPerBuffer = 9 * kMaxItersPerLaunch;
 
 template <typename T>
-__device__ __forceinline__ void fold_events(DrainState<T> ds, int parity) {
-    DrainEvent<T>* ev = ds.events + parity * kEventsPerBuffer;
-    T td = *ds.totaldrain;
-    for (int e = 0; e < kEventsPerBuffer; e++) {
-        if (ev[e].valid) {
-            td = td + ev[e].w_outlet;
-            td = td + ev[e].w_centre;
-            ev[e].valid = 0;
+__device__ __forceinline__ DrainEvent<T>* event_slot(const DrainState<T>& ds, int parity, int outlet, int slot) {
+    return ds.events + ((size_t)parity * ds.n_outlets + outlet) * kEventsPerBuffer + slot;
+}
+
+// index of the outlet at padded (row, col); -1 if none (cannot happen for a marked cell)
+template <typename T>
+__device__ __forceinline__ int outlet_index(const DrainState<T>& ds, int row, int col) {
+    for (int k = 0; k < ds.n_outlets; k++)
+        if (ds.outlet_rc[2 * k] == row && ds.outlet_rc[2 * k + 1] == col) return k;
+    return -1;
+}
+
+// Fold one event buffer: thread t of the calling group takes outlets t, t + nthreads, ...
+template <typename T>
+__device__ __forceinline__ void fold_events(const DrainState<T>& ds, int parity, int t, int nthreads) {
+    for (int k = t; k < ds.n_outlets; k += nthreads) {
+        DrainEvent<T>* ev = event_slot(ds, parity, k, 0);
+        T td = ds.totaldrain[k];
+        bool any = false;
+        for (int e = 0; e < kEventsPerBuffer; e++) {
+            if (ev[e].valid) {
+                td = td + ev[e].w_outlet;
+                td = td + ev[e].w_centre;
+                ev[e].valid = 0;
+                any = true;
+            }
         }
+        if (any) ds.totaldrain[k] = td;
     }
-    *ds.totaldrain = td;
 }
 
 template <typename T>
 __global__ void k_fold_events(DrainState<T> ds, int parity) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) fold_events(ds, parity);
+    if (blockIdx.x == 0) fold_events(ds, parity, (int)threadIdx.x, (int)blockDim.x);
+}
+
+// Mark / unmark outlet cells in the elevation grid (relax.cuh, outlet_mark). `saved` keeps the
+// elevations the marks replace so they can be restored (module change, new outlet set).
+template <typename T>
+__global__ void k_mark_outlets(T* __restrict__ d, Geom g, const int* __restrict__ rc, int n, T* __restrict__ saved, int restore) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int i = rc[2 * k], j = rc[2 * k + 1];
+    if (i < -kPadTop || i >= g.nrows_dev - kPadTop || j < 0 || j > g.C + 1) return;  // not in this solver's rows
+    const size_t a = dev_index(g, i, j);
+    if (restore) d[a] = saved[k];
+    else { saved[k] = d[a]; d[a] = outlet_mark<T>(); }
+}
+
+// A Drain tile whose 3x3 holds outlets (rare): relax it in place and record the contacts. Out of line
+// so that its arrays live on the stack of this call only. `owner`: this CTA owns the centre, so it
+// reports the events (halo copies recompute the same contacts). `slot`: sub-pass slot in the buffer.
+template <typename T>
+__device__ __noinline__ void drain_tile_near_outlets(T* w0, T* w1, T* w2, const T* d0, const T* d1, const T* d2, int j,
+                                                     int mask, DrainState<T> ds, int parity, int slot, int crow, int ccol,
+                                                     bool owner, bool direct) {
+    T evo[8], evc[8];
+    int pos[8];
+    const int n = relax_tile_near_outlets<T>(w0, w1, w2, d0, d1, d2, j, mask, evo, evc, pos);
+    if (!owner) return;
+    for (int i = 0; i < n; i++) {
+        const int k = outlet_index(ds, crow + pos[i] / 3 - 1, ccol + pos[i] % 3 - 1);
+        if (k < 0) continue;
+        if (direct) {  // colour kernel: one launch per sub-pass, a single writer per outlet
+            T td = ds.totaldrain[k];
+            td = td + evo[i];
+            td = td + evc[i];
+            ds.totaldrain[k] = td;
+        } else {
+            DrainEvent<T>* ev = event_slot(ds, parity, k, slot);
+            ev->w_outlet = evo[i];
+            ev->w_centre = evc[i];
+            ev->valid = 1;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -334,19 +395,10 @@ k_colour(T* __restrict__ w, const T* __restrict__ d, Geom g, int oi, int oj, Dra
     T* w1 = w + c;
     const T* d1 = d + c;
     if (MODULE == kDrain) {
-        const int orow = ds.drainrow - row, ocol = ds.draincol - col;
-        if (orow >= -1 && orow <= 1 && ocol >= -1 && ocol <= 1) {
-            if (orow == 0 && ocol == 0) return;  // the outlet is never a centre (src/runoff.cl:179)
-            T evo, evc;
-            bool drained;
-            relax_tile_at_outlet<T>(w1 - g.pitch, w1, w1 + g.pitch, d1 - g.pitch, d1, d1 + g.pitch, 0,
-                                    orow, ocol, &evo, &evc, &drained);
-            if (drained) {  // single writer per sub-pass
-                T td = *ds.totaldrain;
-                td = td + evo;
-                td = td + evc;
-                *ds.totaldrain = td;
-            }
+        const int mask = outlet_mask_3x3<T>(d1 - g.pitch, d1, d1 + g.pitch, 0);
+        if (mask) {
+            drain_tile_near_outlets<T>(w1 - g.pitch, w1, w1 + g.pitch, d1 - g.pitch, d1, d1 + g.pitch, 0, mask, ds, 0, 0,
+                                       row, col, true, true);
             return;
         }
     }
@@ -444,13 +496,25 @@ k_fused(const FusedParams<T> p) {
     MwTile<CFG> tile;
     tile.init(strip, chunk, p.chunk_triples, p.total_triples);
 
-    if (MODULE == kDrain && blockIdx.x == 0 && tid == 0) fold_events(p.ds, p.launch_parity ^ 1);
+    if (MODULE == kDrain && blockIdx.x == 0) fold_events(p.ds, p.launch_parity ^ 1, tid, NTHREADS + 32);
 
+    // Drain: does any outlet lie in the rows and columns this CTA stages? (If not, no tile of this CTA
+    // can see an outlet mark and the per-tile test is skipped.)
+    __shared__ int s_cta_has_outlets;
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; i++) mbar_init(&bars[i], 1);
         fence_mbar_init();
+        s_cta_has_outlets = 0;
     }
     __syncthreads();
+    if (MODULE == kDrain) {
+        for (int k = tid; k < p.ds.n_outlets; k += NTHREADS + 32) {
+            const int orow = p.ds.outlet_rc[2 * k], ocol = p.ds.outlet_rc[2 * k + 1];
+            if (orow >= 3 * tile.m_lo && orow <= 3 * tile.m_hi + 2 && ocol >= tile.x0 && ocol < tile.x0 + W) s_cta_has_outlets = 1;
+        }
+        __syncthreads();
+    }
+    const bool cta_has_outlets = MODULE == kDrain && s_cta_has_outlets != 0;
 
     constexpr uint32_t kRowBytes = W * sizeof(T);
     // device column of window column 0; multiple of 4 elements by construction
@@ -581,16 +645,19 @@ k_fused(const FusedParams<T> p) {
             int s2 = s1 + 1; if (s2 == NRING) s2 = 0;
             wrow[k][0] = ring_w + s0 * W; wrow[k][1] = ring_w + s1 * W; wrow[k][2] = ring_w + s2 * W;
             slow[k] = false;
-            if (MODULE == kDrain) {  // tiles that can touch the outlet take the shared-memory path
-                const int c0 = tile.x0 + it_col[k] - 1;
-                slow[k] = p.ds.drainrow >= row0[k] && p.ds.drainrow <= row0[k] + 2 && p.ds.draincol >= c0 && p.ds.draincol <= c0 + 4;
-            }
-            if (run[k] && !slow[k]) {
+            if (run[k]) {
                 const int jl = it_col[k] - 1;
 #pragma unroll
                 for (int r = 0; r < 3; r++) {
 #pragma unroll
                     for (int cc = 0; cc < 5; cc++) dd[k][r][cc] = wrow[k][r][DOFF + jl + cc];
+                }
+                if (cta_has_outlets) {  // tiles whose 3x5 elevation window holds an outlet mark take the shared-memory path
+#pragma unroll
+                    for (int r = 0; r < 3; r++) {
+#pragma unroll
+                        for (int cc = 0; cc < 5; cc++) slow[k] = slow[k] || is_outlet(dd[k][r][cc]);
+                    }
                 }
             }
         }
@@ -620,21 +687,12 @@ k_fused(const FusedParams<T> p) {
                 const int j = it_col[k] + COFS;  // centre column inside the window
                 if (MODULE == kDrain && run[k] && slow[k]) {
                     const int crow = row0[k] + 1, ccol = tile.x0 + j;
-                    const int orow = p.ds.drainrow - crow, ocol = p.ds.draincol - ccol;
                     T* w0 = wrow[k][0]; T* w1 = wrow[k][1]; T* w2 = wrow[k][2];
-                    if (orow >= -1 && orow <= 1 && ocol >= -1 && ocol <= 1) {
-                        if (orow != 0 || ocol != 0) {
-                            T evo, evc;
-                            bool drained;
-                            relax_tile_at_outlet<T>(w0, w1, w2, w0 + DOFF, w1 + DOFF, w2 + DOFF, j, orow, ocol, &evo, &evc, &drained);
-                            // only the CTA that owns the centre reports the event (halo copies recompute it)
-                            if (drained && tile.owns_row(crow) && tile.owns_col(ccol)) {
-                                DrainEvent<T>* ev = p.ds.events + p.launch_parity * kEventsPerBuffer + (it_ph[k] / 3) * 9 + it_q[k] * 3 + COFS;
-                                ev->w_outlet = evo;
-                                ev->w_centre = evc;
-                                ev->valid = 1;
-                            }
-                        }
+                    const int mask = outlet_mask_3x3<T>(w0 + DOFF, w1 + DOFF, w2 + DOFF, j);
+                    if (mask) {
+                        drain_tile_near_outlets<T>(w0, w1, w2, w0 + DOFF, w1 + DOFF, w2 + DOFF, j, mask, p.ds, p.launch_parity,
+                                                   (it_ph[k] / 3) * 9 + it_q[k] * 3 + COFS, crow, ccol,
+                                                   tile.owns_row(crow) && tile.owns_col(ccol), false);
                     } else {
                         relax_tile<T, MODULE>(w0, w1, w2, w0 + DOFF, w1 + DOFF, w2 + DOFF, j);
                     }
@@ -743,7 +801,7 @@ k_resident(const ResidentParams<T> p) {
     for (int it = 0; it < p.n_iters; it++) {
         const T* __restrict__ win = p.w[cur];
         T* __restrict__ wout = p.w[cur ^ 1];
-        if (MODULE == kDrain && blockIdx.x == 0 && tid == 0) fold_events(p.ds, parity ^ 1);
+        if (MODULE == kDrain && blockIdx.x == 0) fold_events(p.ds, parity ^ 1, tid, NTHREADS);
         for (int k = tid; k < SR * SC; k += NTHREADS) {
             const int i = k / SC, j = k - i * SC;
             sw[k] = win[base + (size_t)i * pitch + j];
@@ -759,21 +817,12 @@ k_resident(const ResidentParams<T> p) {
                 T* w0 = sw + i * SC; T* w1 = w0 + SC; T* w2 = w1 + SC;
                 const T* d0 = sd + i * SC; const T* d1 = d0 + SC; const T* d2 = d1 + SC;
                 if (MODULE == kDrain) {
-                    const int crow = r0 + i + 1, ccol = c0 + j;
-                    const int orow = p.ds.drainrow - crow, ocol = p.ds.draincol - ccol;
-                    if (orow >= -1 && orow <= 1 && ocol >= -1 && ocol <= 1) {
-                        if (orow != 0 || ocol != 0) {
-                            T evo, evc;
-                            bool drained;
-                            relax_tile_at_outlet<T>(w0, w1, w2, d0, d1, d2, j, orow, ocol, &evo, &evc, &drained);
-                            // only the CTA that owns the centre reports the contact (halo copies recompute it)
-                            if (drained && crow >= r_own && crow < r_own + p.TR && ccol >= c_own && ccol < c_own + p.TC) {
-                                DrainEvent<T>* ev = p.ds.events + parity * kEventsPerBuffer + sub;
-                                ev->w_outlet = evo;
-                                ev->w_centre = evc;
-                                ev->valid = 1;
-                            }
-                        }
+                    const int mask = outlet_mask_3x3<T>(d0, d1, d2, j);
+                    if (mask) {
+                        const int crow = r0 + i + 1, ccol = c0 + j;
+                        // only the CTA that owns the centre reports the contact (halo copies recompute it)
+                        drain_tile_near_outlets<T>(w0, w1, w2, d0, d1, d2, j, mask, p.ds, parity, sub, crow, ccol,
+                                                   crow >= r_own && crow < r_own + p.TR && ccol >= c_own && ccol < c_own + p.TC, false);
                         continue;
                     }
                 }
@@ -790,7 +839,7 @@ k_resident(const ResidentParams<T> p) {
         cur ^= 1;
         parity ^= 1;
     }
-    if (MODULE == kDrain && blockIdx.x == 0 && tid == 0) fold_events(p.ds, parity ^ 1);
+    if (MODULE == kDrain && blockIdx.x == 0) fold_events(p.ds, parity ^ 1, tid, NTHREADS);
 }
 
 }  // namespace wdpm

@@ -259,49 +259,74 @@ WDPM_HD bool relax_tile(T* w0, T* w1, T* w2, const T* d0, const T* d1, const T* 
     return true;
 }
 
-// Drain, centre adjacent to the outlet (rare: at most 8 centres per iteration).
-// (orow, ocol) is the outlet's position relative to the centre, each in {-1,0,1},
-// not both 0. The outlet test precedes the height test (src/runoff.cl:104-111):
+// Drain outlets. The reference has exactly one outlet (WDPMCL.c:1005-1017); this solver takes a SET
+// of outlet cells (BASELINE configs[4]; one outlet reproduces the reference). The solver marks an
+// outlet cell in its elevation grid with -S (S = invalid_elevation): runoffdrain never reads an
+// outlet's elevation - the outlet test precedes the height test (runoff.cl:104-111) and an outlet
+// is never a centre (runoff.cl:179) - so the mark costs no information, keeps the cell "valid" for
+// the reductions, and lets every kernel recognise an outlet from the data it already holds.
+template <typename T>
+WDPM_HD T outlet_mark() { return -invalid_elevation<T>(); }
+template <typename T>
+WDPM_HD bool is_outlet(T d) { return d == outlet_mark<T>(); }
+
+// Which cells of the 3x3 around (w1, d1)[j] are outlets: bit (a+1)*3 + (b+1) for row offset a,
+// column offset b (bit 4 = the centre).
+template <typename T>
+WDPM_HD int outlet_mask_3x3(const T* d0, const T* d1, const T* d2, int j) {
+    int m = 0;
+    const T* dr[3] = {d0, d1, d2};
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++)
+            if (is_outlet(dr[a][j + b - 1])) m |= 1 << (a * 3 + b);
+    return m;
+}
+
+// Drain tile with outlets among its cells (rare). `mask` = outlet_mask_3x3. The outlet test precedes
+// the height test (src/runoff.cl:104-111):
 //   totaldrain = totaldrain + w[outlet] + w[centre]; both set to 0; the walk goes on.
-// The two addends are returned so the caller can fold them into totaldrain in
-// sub-pass order: *ev_outlet = w[outlet], *ev_centre = w[centre] at that moment.
-// Kept out of line on the device: it runs for at most eight tiles per iteration, and inlining its
-// pointer tables into the hot loop costs every thread registers (and spills).
+// Each contact's two addends are returned so the caller can fold them into that outlet's total in
+// sub-pass order: ev_outlet[i] = w[outlet], ev_centre[i] = w[centre] at that moment, ev_pos[i] = the
+// outlet's bit position in the 3x3. Returns the number of contacts (<= 8).
+// Kept out of line on the device: inlining its pointer tables into the hot loop costs every thread
+// registers (and spills).
 #ifdef __CUDACC__
 #define WDPM_RARE __host__ __device__ __noinline__
 #else
 #define WDPM_RARE inline
 #endif
 template <typename T>
-WDPM_RARE bool relax_tile_at_outlet(T* w0, T* w1, T* w2, const T* d0, const T* d1, const T* d2, int j,
-                                  int orow, int ocol, T* ev_outlet, T* ev_centre, bool* drained) {
-    *drained = false;
+WDPM_RARE int relax_tile_near_outlets(T* w0, T* w1, T* w2, const T* d0, const T* d1, const T* d2, int j,
+                                      int mask, T* ev_outlet, T* ev_centre, int* ev_pos) {
+    if (mask & 16) return 0;  // the centre is an outlet: never a centre (src/runoff.cl:179)
     T wc = w1[j];
-    if (!(wc > T(0))) return false;
+    if (!(wc > T(0))) return 0;
     const T dc = d1[j];
-    if (!is_valid_elevation(dc)) return false;
+    if (!is_valid_elevation(dc)) return 0;
     T* wr[3] = {w0, w1, w2};
     const T* dr[3] = {d0, d1, d2};
-    for (int a = -1; a <= 1; a++) {
-        for (int b = -1; b <= 1; b++) {
-            if (a == 0 && b == 0) continue;
-            const T dn = dr[a + 1][j + b];
+    int n = 0;
+    for (int a = 0; a < 3; a++) {
+        for (int b = 0; b < 3; b++) {
+            if (a == 1 && b == 1) continue;
+            const T dn = dr[a][j + b - 1];
             if (!is_valid_elevation(dn)) continue;
-            T wn = wr[a + 1][j + b];
-            if (a == orow && b == ocol) {
-                *ev_outlet = wn;
-                *ev_centre = wc;
-                *drained = true;
+            T wn = wr[a][j + b - 1];
+            if (mask & (1 << (a * 3 + b))) {
+                ev_outlet[n] = wn;
+                ev_centre[n] = wc;
+                ev_pos[n] = a * 3 + b;
+                n++;
                 wn = T(0);
                 wc = T(0);
             } else {
                 push<T, kDrain>(dc, wc, dn, wn);
             }
-            wr[a + 1][j + b] = wn;
+            wr[a][j + b - 1] = wn;
         }
     }
     w1[j] = wc;
-    return true;
+    return n;
 }
 
 }  // namespace wdpm

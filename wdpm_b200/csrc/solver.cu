@@ -158,9 +158,14 @@ struct wdpm_solver {
     int cur = 0;
     bool have_dem = false;
 
-    void* totaldrain = nullptr;  // device scalar (T)
-    void* events = nullptr;      // DrainEvent<T>[2][kEventsPerBuffer]
-    int drainrow = -10, draincol = -10;  // local padded rows (may lie outside a stripe)
+    // Drain outlets (kernels.cuh "Drain bookkeeping"): capacity kMaxOutlets
+    void* totaldrain = nullptr;    // T[kMaxOutlets] per-outlet accumulators
+    void* events = nullptr;        // DrainEvent<T>[2][n_outlets][kEventsPerBuffer]
+    void* saved_elev = nullptr;    // T[kMaxOutlets] elevations under the outlet marks
+    int* d_outlet_rc = nullptr;    // int[kMaxOutlets][2] padded (row, col), rows local to this solver
+    std::vector<int> outlet_rc;    // host copy of d_outlet_rc
+    int n_outlets = 0;
+    bool marks_applied = false;
     bool have_outlet = false;
     int launch_parity = 0;
 
@@ -202,10 +207,12 @@ DrainState<T> drain_state(wdpm_solver* s) {
     DrainState<T> ds;
     ds.totaldrain = static_cast<T*>(s->totaldrain);
     ds.events = static_cast<DrainEvent<T>*>(s->events);
-    ds.drainrow = s->drainrow;
-    ds.draincol = s->draincol;
+    ds.outlet_rc = s->d_outlet_rc;
+    ds.n_outlets = s->n_outlets;
     return ds;
 }
+
+constexpr int kMaxOutlets = WDPM_MAX_OUTLETS;
 
 int grid_for(long long n, int threads, int sm_count) {
     long long b = (n + threads - 1) / threads;
@@ -292,7 +299,7 @@ int fused_iterations(wdpm_solver* s, int n) {
         }
     }
     if (s->module == WDPM_DRAIN && n_launch > 0) {
-        k_fold_events<T><<<1, 32, 0, s->stream>>>(drain_state<T>(s), s->launch_parity ^ 1);
+        k_fold_events<T><<<1, 256, 0, s->stream>>>(drain_state<T>(s), s->launch_parity ^ 1);
         s->launches++;
         CUDA_TRY(cudaGetLastError());
     }
@@ -319,7 +326,7 @@ int fused_launch_only(wdpm_solver* s) {
     s->cur ^= 1;
     s->launch_parity ^= 1;
     if (s->module == WDPM_DRAIN) {
-        k_fold_events<T><<<1, 32, 0, s->stream>>>(drain_state<T>(s), s->launch_parity ^ 1);
+        k_fold_events<T><<<1, 256, 0, s->stream>>>(drain_state<T>(s), s->launch_parity ^ 1);
         s->launches++;
         CUDA_TRY(cudaGetLastError());
     }
@@ -405,10 +412,12 @@ int block_end_t(wdpm_solver* s, wdpm_block_result* out) {
     s->launches += 2;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(s->h_result, s->d_result, sizeof(BlockPartial), cudaMemcpyDeviceToHost, s->stream));
-    T td = T(0);
-    CUDA_TRY(cudaMemcpyAsync(&td, s->totaldrain, sizeof(T), cudaMemcpyDeviceToHost, s->stream));
+    std::vector<T> tds((size_t)(s->n_outlets > 0 ? s->n_outlets : 1), T(0));
+    CUDA_TRY(cudaMemcpyAsync(tds.data(), s->totaldrain, sizeof(T) * tds.size(), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
+    T td = tds[0];  // one outlet: the reference's totaldrain; a set: summed in outlet order, solver precision
+    for (size_t k = 1; k < tds.size(); k++) td = td + tds[k];
     s->in_block = false;
     if (out) {
         out->max_diff = s->h_result->max_diff;
@@ -477,6 +486,21 @@ void choose_chunks(wdpm_solver* s, int K, int NT, int minb, int forced_rows) {
     }
     s->chunk_triples = best_ct;
     s->n_chunks = (total + best_ct - 1) / best_ct;
+}
+
+// Put the outlet marks into the elevation grid (on = true) or take them out again, restoring the
+// elevations they replaced (kernels.cuh, k_mark_outlets). Idempotent.
+int apply_outlet_marks(wdpm_solver* s, bool on) {
+    if (s->n_outlets == 0 || s->marks_applied == on) return WDPM_OK;
+    const int n = s->n_outlets, blocks = (n + 127) / 128;
+    if (s->dtype == WDPM_F64)
+        k_mark_outlets<double><<<blocks, 128, 0, s->stream>>>(static_cast<double*>(s->dem), s->g, s->d_outlet_rc, n, static_cast<double*>(s->saved_elev), on ? 0 : 1);
+    else
+        k_mark_outlets<float><<<blocks, 128, 0, s->stream>>>(static_cast<float*>(s->dem), s->g, s->d_outlet_rc, n, static_cast<float*>(s->saved_elev), on ? 0 : 1);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    s->marks_applied = on;
+    return WDPM_OK;
 }
 
 }  // namespace
@@ -658,9 +682,11 @@ int wdpm_create(const wdpm_config* cfg, wdpm_solver** out) {
         s->device_bytes += (long long)grid_bytes;
     }
     s->reduce_blocks = s->sm_count * 8;
-    const size_t ev_bytes = 2 * kEventsPerBuffer * (s->dtype == WDPM_F64 ? sizeof(DrainEvent<double>) : sizeof(DrainEvent<float>));
+    const size_t ev_bytes = (size_t)2 * kMaxOutlets * kEventsPerBuffer * (s->dtype == WDPM_F64 ? sizeof(DrainEvent<double>) : sizeof(DrainEvent<float>));
     if ((e = cudaMalloc((void**)&s->flags, sizeof(HaloFlags))) != cudaSuccess) return cleanup(WDPM_E_NOMEM, cudaGetErrorString(e));
-    if ((e = cudaMalloc(&s->totaldrain, 8)) != cudaSuccess || (e = cudaMalloc(&s->events, ev_bytes)) != cudaSuccess ||
+    if ((e = cudaMalloc(&s->totaldrain, 8 * kMaxOutlets)) != cudaSuccess || (e = cudaMalloc(&s->events, ev_bytes)) != cudaSuccess ||
+        (e = cudaMalloc(&s->saved_elev, 8 * kMaxOutlets)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&s->d_outlet_rc, sizeof(int) * 2 * kMaxOutlets)) != cudaSuccess ||
         (e = cudaMalloc((void**)&s->partials, sizeof(BlockPartial) * s->reduce_blocks)) != cudaSuccess ||
         (e = cudaMalloc((void**)&s->d_result, sizeof(BlockPartial))) != cudaSuccess ||
         (e = cudaMalloc((void**)&s->outlet_partials, sizeof(OutletCand) * s->reduce_blocks)) != cudaSuccess ||
@@ -676,7 +702,7 @@ int wdpm_create(const wdpm_config* cfg, wdpm_solver** out) {
     if ((e = cudaMemsetAsync(s->w[0], 0, grid_bytes, s->stream)) != cudaSuccess ||
         (e = cudaMemsetAsync(s->w[1], 0, grid_bytes, s->stream)) != cudaSuccess ||
         (e = cudaMemsetAsync(s->oldw, 0, grid_bytes, s->stream)) != cudaSuccess ||
-        (e = cudaMemsetAsync(s->totaldrain, 0, 8, s->stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(s->totaldrain, 0, 8 * kMaxOutlets, s->stream)) != cudaSuccess ||
         (e = cudaMemsetAsync(s->flags, 0, sizeof(HaloFlags), s->stream)) != cudaSuccess ||
         (e = cudaMemsetAsync(s->events, 0, ev_bytes, s->stream)) != cudaSuccess)
         return cleanup(WDPM_E_CUDA, cudaGetErrorString(e));
@@ -698,7 +724,7 @@ int wdpm_destroy(wdpm_solver* s) {
             cudaIpcCloseMemHandle(peer->flags);
         }
     if (s->flags) cudaFree(s->flags);
-    void* ptrs[] = {s->dem, s->w[0], s->w[1], s->oldw, s->totaldrain, s->events, s->partials, s->d_result, s->outlet_partials, s->d_outlet};
+    void* ptrs[] = {s->dem, s->w[0], s->w[1], s->oldw, s->totaldrain, s->events, s->saved_elev, s->d_outlet_rc, s->partials, s->d_result, s->outlet_partials, s->d_outlet};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->h_result) cudaFreeHost(s->h_result);
@@ -740,6 +766,9 @@ int wdpm_upload(wdpm_solver* s, const void* dem, const void* water) {
         CUDA_TRY(cudaGetLastError());
     }
     s->have_dem = true;
+    s->marks_applied = false;  // the upload replaced the marked cells
+    rc = apply_outlet_marks(s, true);
+    if (rc) return rc;
     return wdpm_upload_water(s, water);
 }
 
@@ -814,6 +843,8 @@ int wdpm_find_outlet(wdpm_solver* s, int32_t* drainrow, int32_t* draincol, doubl
     if (!s) return fail(WDPM_E_ARG, "null solver");
     if (!s->have_dem) return fail(WDPM_E_STATE, "upload first");
     CUDA_TRY(cudaSetDevice(s->device));
+    int rc = apply_outlet_marks(s, false);  // search the true elevations
+    if (rc) return rc;
     if (s->dtype == WDPM_F64)
         k_find_outlet_stage1<double, 256><<<s->reduce_blocks, 256, 0, s->stream>>>(static_cast<const double*>(s->dem), s->g, s->outlet_partials);
     else
@@ -824,23 +855,40 @@ int wdpm_find_outlet(wdpm_solver* s, int32_t* drainrow, int32_t* draincol, doubl
     OutletCand c;
     CUDA_TRY(cudaMemcpyAsync(&c, s->d_outlet, sizeof(c), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    if (c.index < 0) return fail(WDPM_E_STATE, "no cell with elevation > 0: no outlet");
-    s->drainrow = (int)(c.index / (s->g.C + 2));
-    s->draincol = (int)(c.index % (s->g.C + 2));
-    s->have_outlet = true;
-    if (drainrow) *drainrow = s->drainrow + s->G;
-    if (draincol) *draincol = s->draincol;
+    if (c.index < 0) { apply_outlet_marks(s, true); return fail(WDPM_E_STATE, "no cell with elevation > 0: no outlet"); }
+    const int32_t row = (int32_t)(c.index / (s->g.C + 2)) + s->G, col = (int32_t)(c.index % (s->g.C + 2));
+    if (drainrow) *drainrow = row;
+    if (draincol) *draincol = col;
     if (min_elevation) *min_elevation = c.elev;
-    return WDPM_OK;
+    return wdpm_set_outlets(s, 1, &row, &col);
 }
 
-int wdpm_set_outlet(wdpm_solver* s, int32_t drainrow, int32_t draincol) {
-    if (!s) return fail(WDPM_E_ARG, "null solver");
-    if (drainrow < 0 || drainrow > s->cfg.rows + 1 || draincol < 0 || draincol > s->g.C + 1) return fail(WDPM_E_ARG, "outlet outside the padded grid");
-    s->drainrow = drainrow - s->G;  // kernels work in the stripe's local rows
+int wdpm_set_outlet(wdpm_solver* s, int32_t drainrow, int32_t draincol) { return wdpm_set_outlets(s, 1, &drainrow, &draincol); }
+
+int wdpm_set_outlets(wdpm_solver* s, int32_t n, const int32_t* rows, const int32_t* cols) {
+    if (!s || (n > 0 && (!rows || !cols))) return fail(WDPM_E_ARG, "null argument");
+    if (s->module != WDPM_DRAIN) return fail(WDPM_E_STATE, "outlets belong to the Drain module");
+    if (n < 1 || n > kMaxOutlets) return fail(WDPM_E_ARG, "number of outlets must be in 1..WDPM_MAX_OUTLETS");
+    if (s->in_block) return fail(WDPM_E_STATE, "a block is open");
+    for (int k = 0; k < n; k++) {
+        if (rows[k] < 0 || rows[k] > s->cfg.rows + 1 || cols[k] < 0 || cols[k] > s->g.C + 1) return fail(WDPM_E_ARG, "outlet outside the padded grid");
+        for (int q = 0; q < k; q++)
+            if (rows[q] == rows[k] && cols[q] == cols[k]) return fail(WDPM_E_ARG, "duplicate outlet");
+    }
+    CUDA_TRY(cudaSetDevice(s->device));
+    int rc = apply_outlet_marks(s, false);  // restore the cells of the previous set
+    if (rc) return rc;
+    s->outlet_rc.resize((size_t)2 * n);
+    for (int k = 0; k < n; k++) {
+        s->outlet_rc[2 * k] = rows[k] - s->G;  // kernels work in the stripe's local rows (may lie outside the stripe)
+        s->outlet_rc[2 * k + 1] = cols[k];
+    }
+    s->n_outlets = n;
     s->have_outlet = true;
-    s->draincol = draincol;
-    return WDPM_OK;
+    CUDA_TRY(cudaMemcpyAsync(s->d_outlet_rc, s->outlet_rc.data(), sizeof(int) * 2 * n, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->events, 0, (size_t)2 * n * kEventsPerBuffer * (s->dtype == WDPM_F64 ? sizeof(DrainEvent<double>) : sizeof(DrainEvent<float>)), s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return s->have_dem ? apply_outlet_marks(s, true) : WDPM_OK;
 }
 
 int wdpm_set_total_drain(wdpm_solver* s, double value) {
@@ -848,19 +896,39 @@ int wdpm_set_total_drain(wdpm_solver* s, double value) {
     CUDA_TRY(cudaSetDevice(s->device));
     double v64 = value;
     float v32 = (float)value;
+    CUDA_TRY(cudaMemsetAsync(s->totaldrain, 0, 8 * kMaxOutlets, s->stream));  // the value goes to the first outlet's total
     CUDA_TRY(cudaMemcpyAsync(s->totaldrain, s->dtype == WDPM_F64 ? (void*)&v64 : (void*)&v32, s->esize, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     return WDPM_OK;
 }
 
+int wdpm_get_outlet_drains(wdpm_solver* s, double* values, int32_t n) {
+    if (!s || !values) return fail(WDPM_E_ARG, "null argument");
+    if (n < 1 || n > kMaxOutlets) return fail(WDPM_E_ARG, "n out of range");
+    CUDA_TRY(cudaSetDevice(s->device));
+    std::vector<double> v64((size_t)n);
+    std::vector<float> v32((size_t)n);
+    CUDA_TRY(cudaMemcpyAsync(s->dtype == WDPM_F64 ? (void*)v64.data() : (void*)v32.data(), s->totaldrain, s->esize * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    for (int k = 0; k < n; k++) values[k] = s->dtype == WDPM_F64 ? v64[k] : (double)v32[k];
+    return WDPM_OK;
+}
+
 int wdpm_get_total_drain(wdpm_solver* s, double* value) {
     if (!s || !value) return fail(WDPM_E_ARG, "null argument");
-    CUDA_TRY(cudaSetDevice(s->device));
-    double v64 = 0;
-    float v32 = 0;
-    CUDA_TRY(cudaMemcpyAsync(s->dtype == WDPM_F64 ? (void*)&v64 : (void*)&v32, s->totaldrain, s->esize, cudaMemcpyDeviceToHost, s->stream));
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
-    *value = s->dtype == WDPM_F64 ? v64 : (double)v32;
+    const int n = s->n_outlets > 0 ? s->n_outlets : 1;
+    std::vector<double> v((size_t)n);
+    int rc = wdpm_get_outlet_drains(s, v.data(), n);
+    if (rc) return rc;
+    if (s->dtype == WDPM_F64) {
+        double t = v[0];
+        for (int k = 1; k < n; k++) t = t + v[k];
+        *value = t;
+    } else {
+        float t = (float)v[0];
+        for (int k = 1; k < n; k++) t = t + (float)v[k];
+        *value = (double)t;
+    }
     return WDPM_OK;
 }
 
@@ -1006,6 +1074,11 @@ int wdpm_stripe_upload(wdpm_solver* s, const void* dem_band, const void* water_b
     CUDA_TRY(cudaMemsetAsync(s->flags, 0, sizeof(HaloFlags), s->stream));
     s->epoch = 0;
     s->have_dem = true;
+    s->marks_applied = false;  // the upload replaced the marked cells
+    {
+        const int rc = apply_outlet_marks(s, true);
+        if (rc) return rc;
+    }
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     return WDPM_OK;
 }

@@ -183,6 +183,18 @@ class Solver:
     def set_outlet(self, drainrow: int, draincol: int):
         _check(self._lib.wdpm_set_outlet(self._h, C.c_int32(drainrow), C.c_int32(draincol)))
 
+    def set_outlets(self, outlets):
+        """A set of outlet cells [(row, col), ...] in padded coordinates of the whole DEM (extension;
+        one outlet is the reference's Drain)."""
+        rows = (C.c_int32 * len(outlets))(*[int(o[0]) for o in outlets])
+        cols = (C.c_int32 * len(outlets))(*[int(o[1]) for o in outlets])
+        _check(self._lib.wdpm_set_outlets(self._h, C.c_int32(len(outlets)), rows, cols))
+
+    def get_outlet_drains(self, n: int) -> np.ndarray:
+        out = np.zeros(n, dtype=np.float64)
+        _check(self._lib.wdpm_get_outlet_drains(self._h, out.ctypes.data_as(C.POINTER(C.c_double)), C.c_int32(n)))
+        return out
+
     def set_total_drain(self, v: float):
         _check(self._lib.wdpm_set_total_drain(self._h, C.c_double(v)))
 
