@@ -860,10 +860,14 @@ int wdpm_find_outlet(wdpm_solver* s, int32_t* drainrow, int32_t* draincol, doubl
     if (drainrow) *drainrow = row;
     if (draincol) *draincol = col;
     if (min_elevation) *min_elevation = c.elev;
+    if (s->module != WDPM_DRAIN) return WDPM_OK;  // a query only; no outlet to install
     return wdpm_set_outlets(s, 1, &row, &col);
 }
 
-int wdpm_set_outlet(wdpm_solver* s, int32_t drainrow, int32_t draincol) { return wdpm_set_outlets(s, 1, &drainrow, &draincol); }
+int wdpm_set_outlet(wdpm_solver* s, int32_t drainrow, int32_t draincol) {
+    if (s && s->module != WDPM_DRAIN) return WDPM_OK;  // only Drain kernels look at outlets
+    return wdpm_set_outlets(s, 1, &drainrow, &draincol);
+}
 
 int wdpm_set_outlets(wdpm_solver* s, int32_t n, const int32_t* rows, const int32_t* cols) {
     if (!s || (n > 0 && (!rows || !cols))) return fail(WDPM_E_ARG, "null argument");
