@@ -31,7 +31,7 @@ __device__ __forceinline__ void push_cand(double dc, double& wc, double dn, doub
     }
 }
 template <int V>
-__device__ __forceinline__ void relax_cand(double (&w)[3][3], const double (&d)[3][5]) {
+__device__ __forceinline__ void relax_cand(double (&w)[3][5], const double (&d)[3][5]) {
     const double dc = d[1][1];
     double wc = w[1][1];
     push_cand<V>(dc, wc, d[0][0], w[0][0]);
@@ -47,17 +47,17 @@ __device__ __forceinline__ void relax_cand(double (&w)[3][3], const double (&d)[
 
 template <int MODE>
 __global__ void k(double* out, long long* cyc, const double* in, int reps) {
-    double w[3][3], d[3][5];
+    double w[3][5], d[3][5];
     for (int r = 0; r < 3; r++) {
-        for (int c = 0; c < 3; c++) w[r][c] = in[(threadIdx.x * 31 + r * 3 + c) % 256];
+        for (int c = 0; c < 5; c++) w[r][c] = in[(threadIdx.x * 31 + r * 3 + c) % 256];
         for (int c = 0; c < 5; c++) d[r][c] = 500.0 + in[(threadIdx.x * 17 + r * 5 + c) % 256];
     }
     __syncthreads();
     long long t0 = clock64();
 #pragma unroll 1
     for (int i = 0; i < reps; i++) {
-        if (MODE == 0) relax_window<double, kAdd, 0>(w, d);
-        if (MODE == 1) relax_window_add_fast<double, 0>(w, d);
+        if (MODE == 0) relax_window5<double, kAdd, 0, false>(w, d);
+        if (MODE == 1) relax_window5<double, kAdd, 0, true>(w, d);
         if (MODE == 2) {  // 9 independent DADDs
 #pragma unroll
             for (int r = 0; r < 3; r++)

@@ -465,6 +465,14 @@ constexpr size_t fused_smem_bytes() {
 // OPT bit 0 (fp64 Add only; in fp32 the predicated-add form measured faster): cap-free, sign-gated neighbour step (relax.cuh, push_add_fast) - 12 instead
 // of 15 instructions per neighbour, 7 instead of 9 of them on the FP64 pipe.
 constexpr int kOptAddFast = 1;
+// OPT bit 1: REGISTER REALLOCATION. The register file hands registers to groups of four warps, so a
+// CTA of 24 compute warps + 1 data-movement warp is budgeted as 28 warps: 72 registers per thread,
+// where 24 warps alone could have 80 (measured: scripts/micro/reg_granularity.cu). With this bit the
+// CTA is launched with a whole fourth warp group (4 warps, one of them the data-movement warp, the
+// others exit at once); that group gives its registers back (setmaxnreg.dec to 24) and the compute
+// warps take them (setmaxnreg.inc to 80): 28*72 = 4*24 + 24*80.
+constexpr int kOptRegRealloc = 2;
+__host__ __device__ constexpr int fused_extra_threads(int opt) { return (opt & kOptRegRealloc) ? 128 : 32; }
 
 #ifdef WDPM_TIMELINE
 // Developer probe (never compiled into the product library): per-warp clock64 stamps of one CTA.
@@ -482,8 +490,11 @@ __device__ int g_timeline_cta = 300, g_timeline_step0 = 100;
 #endif
 
 template <typename T, int MODULE, typename CFG, int NTHREADS, int MINB, int OPT = 0>
-__global__ void __launch_bounds__(NTHREADS + 32, MINB)
+__global__ void __launch_bounds__(NTHREADS + fused_extra_threads(OPT), MINB)
 k_fused(const FusedParams<T> p) {
+    constexpr int NALL = NTHREADS + fused_extra_threads(OPT);  // threads of the CTA
+    constexpr bool REALLOC = (OPT & kOptRegRealloc) != 0;
+    static_assert(!REALLOC || (NTHREADS == 768 && MINB == 1), "register reallocation is sized for 24 compute warps, one CTA per SM");
     constexpr int W = CFG::W, NT = CFG::NT, NPH = CFG::NPH, NRING = CFG::NRING, NSTAGE = CFG::NSTAGE, PF = CFG::PF;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* ring_w = reinterpret_cast<T*>(smem_raw);
@@ -496,7 +507,7 @@ k_fused(const FusedParams<T> p) {
     MwTile<CFG> tile;
     tile.init(strip, chunk, p.chunk_triples, p.total_triples);
 
-    if (MODULE == kDrain && blockIdx.x == 0) fold_events(p.ds, p.launch_parity ^ 1, tid, NTHREADS + 32);
+    if (MODULE == kDrain && blockIdx.x == 0) fold_events(p.ds, p.launch_parity ^ 1, tid, NALL);
 
     // Drain: does any outlet lie in the rows and columns this CTA stages? (If not, no tile of this CTA
     // can see an outlet mark and the per-tile test is skipped.)
@@ -508,7 +519,7 @@ k_fused(const FusedParams<T> p) {
     }
     __syncthreads();
     if (MODULE == kDrain) {
-        for (int k = tid; k < p.ds.n_outlets; k += NTHREADS + 32) {
+        for (int k = tid; k < p.ds.n_outlets; k += NALL) {
             const int orow = p.ds.outlet_rc[2 * k], ocol = p.ds.outlet_rc[2 * k + 1];
             if (orow >= 3 * tile.m_lo && orow <= 3 * tile.m_hi + 2 && ocol >= tile.x0 && ocol < tile.x0 + W) s_cta_has_outlets = 1;
         }
@@ -571,6 +582,10 @@ k_fused(const FusedParams<T> p) {
     // Warp specialisation: the last warp only moves data (one elected lane issues the bulk copies),
     // the first NTHREADS threads only compute.
     if (tid >= NTHREADS) {
+        if (REALLOC) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+            if (tid >= NTHREADS + 32) return;  // the rest of the fourth warp group only lent its registers
+        }
         const bool lead = tid == NTHREADS;
         if (lead)
             for (int s = 0; s < PF && s < tile.n_steps; s++) issue_loads(s);
@@ -600,6 +615,8 @@ k_fused(const FusedParams<T> p) {
         }
         return;
     }
+
+    if (REALLOC) asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
 
     // Static work assignment: in every sub-step thread `tid` relaxes tiles number tid,
     // tid+NTHREADS, ... of the NPH*NT*NC tiles (phase-major, then triple slot, then column), so its
@@ -631,7 +648,7 @@ k_fused(const FusedParams<T> p) {
     bool run[IPT], slow[IPT], dirty[IPT];
     int row0[IPT];
     T* wrow[IPT][3];
-    T wt[IPT][3][3], dd[IPT][3][5];
+    T wt[IPT][3][5], dd[IPT][3][5];  // wt: columns COFS..COFS+2 are live in sub-pass COFS
     constexpr int DOFF = NRING * W;  // ring_d = ring_w + DOFF
 
     auto prepare = [&](int s) {  // where step s's tiles live, and their elevation windows
@@ -698,30 +715,25 @@ k_fused(const FusedParams<T> p) {
                     }
                     continue;
                 }
-                if (COFS > 0 && run[k]) {  // slide: drop the published left column, read the entering right column
+                if (COFS > 0 && run[k]) {  // slide: the published left column is dead, read the entering right column
 #pragma unroll
-                    for (int r = 0; r < 3; r++) {
-                        wt[k][r][0] = wt[k][r][1];
-                        wt[k][r][1] = wt[k][r][2];
-                        wt[k][r][2] = wrow[k][r][j + 1];
-                    }
+                    for (int r = 0; r < 3; r++) wt[k][r][COFS + 2] = wrow[k][r][j + 1];
                 }
-                const bool active = run[k] && (wt[k][1][1] > T(0)) && is_valid_elevation(dd[k][1][COFS + 1]);
+                const bool active = run[k] && (wt[k][1][COFS + 1] > T(0)) && is_valid_elevation(dd[k][1][COFS + 1]);
                 if (active) {
-                    if (ADD_FAST) relax_window_add_fast<T, COFS>(wt[k], dd[k]);
-                    else relax_window<T, MODULE, COFS>(wt[k], dd[k]);
+                    relax_window5<T, MODULE, COFS, ADD_FAST>(wt[k], dd[k]);
                     dirty[k] = true;
                 }
                 if (dirty[k]) {
                     if (COFS < 2) {
 #pragma unroll
-                        for (int r = 0; r < 3; r++) wrow[k][r][j - 1] = wt[k][r][0];
+                        for (int r = 0; r < 3; r++) wrow[k][r][j - 1] = wt[k][r][COFS];
                     } else {
 #pragma unroll
                         for (int r = 0; r < 3; r++) {
-                            wrow[k][r][j - 1] = wt[k][r][0];
-                            wrow[k][r][j] = wt[k][r][1];
-                            wrow[k][r][j + 1] = wt[k][r][2];
+                            wrow[k][r][j - 1] = wt[k][r][COFS];
+                            wrow[k][r][j] = wt[k][r][COFS + 1];
+                            wrow[k][r][j + 1] = wt[k][r][COFS + 2];
                         }
                     }
                 }

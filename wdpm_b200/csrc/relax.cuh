@@ -201,37 +201,23 @@ WDPM_HD void push_add_fast(T dc, T& wc, T dn, T& wn) {
     move_if(sign_clear(x), wc, wn, x * T(0.125));
 }
 
-template <typename T, int COFS>
-WDPM_HD void relax_window_add_fast(T (&w)[3][3], const T (&d)[3][5]) {
+// The eight steps on a register window that "slides" one column per colour sub-pass: w and d hold the
+// tile's water / elevations over ALL three positions (3x5); sub-pass COFS works on columns
+// COFS..COFS+2. Indices are compile-time constants, so the slide is register renaming - no moves.
+template <typename T, int MODULE, int COFS, bool FAST>
+WDPM_HD void relax_window5(T (&w)[3][5], const T (&d)[3][5]) {
     const T dc = d[1][COFS + 1];
-    T wc = w[1][1];
-    push_add_fast<T>(dc, wc, d[0][COFS + 0], w[0][0]);
-    push_add_fast<T>(dc, wc, d[0][COFS + 1], w[0][1]);
-    push_add_fast<T>(dc, wc, d[0][COFS + 2], w[0][2]);
-    push_add_fast<T>(dc, wc, d[1][COFS + 0], w[1][0]);
-    push_add_fast<T>(dc, wc, d[1][COFS + 2], w[1][2]);
-    push_add_fast<T>(dc, wc, d[2][COFS + 0], w[2][0]);
-    push_add_fast<T>(dc, wc, d[2][COFS + 1], w[2][1]);
-    push_add_fast<T>(dc, wc, d[2][COFS + 2], w[2][2]);
-    w[1][1] = wc;
-}
-
-// The same eight steps on a register window that slides one column per colour sub-pass:
-// w holds the tile's 3x3 water (rows x cols), d the elevations of the 3x5 cells the tile
-// covers over the three sub-passes; COFS (0,1,2) selects which three elevation columns apply.
-template <typename T, int MODULE, int COFS>
-WDPM_HD void relax_window(T (&w)[3][3], const T (&d)[3][5]) {
-    const T dc = d[1][COFS + 1];
-    T wc = w[1][1];
-    push<T, MODULE>(dc, wc, d[0][COFS + 0], w[0][0]);
-    push<T, MODULE>(dc, wc, d[0][COFS + 1], w[0][1]);
-    push<T, MODULE>(dc, wc, d[0][COFS + 2], w[0][2]);
-    push<T, MODULE>(dc, wc, d[1][COFS + 0], w[1][0]);
-    push<T, MODULE>(dc, wc, d[1][COFS + 2], w[1][2]);
-    push<T, MODULE>(dc, wc, d[2][COFS + 0], w[2][0]);
-    push<T, MODULE>(dc, wc, d[2][COFS + 1], w[2][1]);
-    push<T, MODULE>(dc, wc, d[2][COFS + 2], w[2][2]);
-    w[1][1] = wc;
+    T wc = w[1][COFS + 1];
+#define WDPM_PUSH5(r, c)                                                                     \
+    do {                                                                                     \
+        if (FAST && MODULE == kAdd && sizeof(T) == 8) push_add_fast<T>(dc, wc, d[r][COFS + c], w[r][COFS + c]); \
+        else push<T, MODULE>(dc, wc, d[r][COFS + c], w[r][COFS + c]);                        \
+    } while (0)
+    WDPM_PUSH5(0, 0); WDPM_PUSH5(0, 1); WDPM_PUSH5(0, 2);
+    WDPM_PUSH5(1, 0); WDPM_PUSH5(1, 2);
+    WDPM_PUSH5(2, 0); WDPM_PUSH5(2, 1); WDPM_PUSH5(2, 2);
+#undef WDPM_PUSH5
+    w[1][COFS + 1] = wc;
 }
 
 // The eight neighbour steps of one tile (only meaningful when t.active). FAST selects the fp64 Add

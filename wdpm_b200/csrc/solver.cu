@@ -17,7 +17,7 @@ using namespace wdpm;
 
 namespace {
 
-constexpr int kDefaultVariantF64 = 11;  // 384-column window, two row triples per phase, 24 compute warps, Add fast step
+constexpr int kDefaultVariantF64 = 13;  // 384-column window, two row triples per phase, 24 compute warps at 80 registers, Add fast step
 constexpr int kDefaultVariantF32 = 7;   // 512-column window, two CTAs of 16 compute warps per SM
 constexpr int kDefaultVariantF64Drain = 1;  // Drain's relax step needs more registers than 24 warps leave: 16 warps, 512 columns
 // Grids of a few hundred thousand cells (the reference's basin5 is 482 x 471) cannot fill 148 SMs
@@ -60,7 +60,7 @@ struct FusedVariant {
 
 template <typename T, int MODULE, typename CFG, int NTHREADS, int MINB, int OPT>
 cudaError_t launch_fused(const FusedParams<T>& p, int grid, cudaStream_t st) {
-    k_fused<T, MODULE, CFG, NTHREADS, MINB, OPT><<<grid, NTHREADS + 32, fused_smem_bytes<CFG, T>(), st>>>(p);  // +1 data-movement warp
+    k_fused<T, MODULE, CFG, NTHREADS, MINB, OPT><<<grid, NTHREADS + fused_extra_threads(OPT), fused_smem_bytes<CFG, T>(), st>>>(p);  // + the data-movement warp
     return cudaGetLastError();
 }
 
@@ -110,6 +110,7 @@ const std::vector<FusedVariant<double>>& fused_variants<double>() {
         make_variant<double, MwCfg<384, 2, 1, 1>, 768, 1>(),   // 10: two triples per phase, 24 warps, one tile per thread
         make_variant<double, MwCfg<384, 2, 1, 1>, 768, 1, kOptAddFast>(),  // 11: as 10, Add with the sign gate and cap-free chains
         make_variant<double, MwCfg<64, 1, 1, 1>, 128, 1, kOptAddFast>(),   // 12: test window with the Add fast path
+        make_variant<double, MwCfg<384, 2, 1, 1>, 768, 1, kOptAddFast | kOptRegRealloc>(),  // 13: as 11, compute warps at 80 registers
     };
     return v;
 }
