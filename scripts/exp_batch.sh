@@ -1,6 +1,5 @@
 set -x
 mkdir -p gpurun_out
-nvidia-smi -L
-timeout 1200 python -m pytest tests -q -m gpu > gpurun_out/b10_gpu_tests.log 2>&1; tail -4 gpurun_out/b10_gpu_tests.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 2 --warmup 3 > gpurun_out/bench_r1b_n2.json 2> gpurun_out/bench_r1b_n2.err; tail -c 600 gpurun_out/bench_r1b_n2.json
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 scripts/large_drain.py --size 65536 --blocks 1 --outlets 64 --out gpurun_out/cfg5_drain_65536_2gpu_64outlets.json > gpurun_out/cfg5.log 2>&1; tail -3 gpurun_out/cfg5.log
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "all_variants and float32" > gpurun_out/b11_parity.log 2>&1; tail -3 gpurun_out/b11_parity.log
+for v in 7 14; do timeout 300 python scripts/profile_iterate.py --size 8192 --dtype f32 --iters 200 --add-mm 100 --variant $v 2>&1 | tail -1; done > gpurun_out/b11_f32.txt
+cat gpurun_out/b11_f32.txt

@@ -198,7 +198,7 @@ WDPM_HD void push_add_fast(T dc, T& wc, T dn, T& wn) {
         return;
     }
 #endif
-    move_if(sign_clear(x), wc, wn, x * T(0.125));
+    move_if(sign_clear(h), wc, wn, x * T(0.125));  // dc > sn implies h > 0: the gate can be read off h
 }
 
 // The eight steps on a register window that "slides" one column per colour sub-pass: w and d hold the
