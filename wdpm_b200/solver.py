@@ -17,6 +17,9 @@ ADD, SUBTRACT, DRAIN = 0, 1, 2
 F32, F64 = 0, 1
 KERNEL_AUTO, KERNEL_COLOUR, KERNEL_FUSED, KERNEL_RESIDENT = 0, 1, 2, 3
 MODULES = {"add": ADD, "subtract": SUBTRACT, "drain": DRAIN}
+# the tiling AUTO picks for large fp64 Add/Subtract grids (kDefaultVariantF64 in csrc/solver.cu); tests and
+# smoke() name it to exercise the production kernel on small grids
+PRODUCTION_FUSED_VARIANT_F64 = 13
 
 _PKG = Path(__file__).resolve().parent
 
