@@ -111,6 +111,74 @@ def test_fused_drain_outlet_on_ownership_boundaries(cuda_lib, oracle):
         assert np.array_equal(a, b) and ta == tb, (orow, ocol)
 
 
+def _adversarial_case(rng, rows, cols, dt, kind):
+    """Inputs built to sit on the arithmetic's edges rather than in its middle."""
+    nodata = NODATA
+    if kind == "flat":            # exactly flat terrain: every comparison is a tie broken by water alone
+        d = np.full((rows, cols), 500.0)
+        w = rng.uniform(0, 0.3, d.shape)
+    elif kind == "ulp":           # elevations a few ulps apart, water of the order of one ulp of the elevation
+        d = 500.0 + np.float64(np.spacing(dt(500.0))) * rng.integers(-3, 4, (rows, cols))
+        w = np.float64(np.spacing(dt(500.0))) * rng.uniform(0, 4, d.shape)
+    elif kind == "tiny":          # water from the subnormal range up to millimetres
+        d = (500 + 3 * rng.standard_normal((rows, cols))).round(4)
+        lo = -44.0 if dt == np.float32 else -320.0
+        w = 10.0 ** rng.uniform(lo, -3, d.shape)
+    elif kind == "negative":      # negative and zero elevations (Drain's outlet rule wants dem > 0)
+        d = (-50 + 30 * rng.standard_normal((rows, cols))).round(3)
+        d[rng.uniform(size=d.shape) < 0.1] = 0.0
+        w = rng.uniform(0, 2.0, d.shape)
+    elif kind == "all_nodata":
+        d = np.full((rows, cols), nodata)
+        w = rng.uniform(0, 0.3, d.shape)
+    else:                         # "dry": nothing to move
+        d = (500 + 3 * rng.standard_normal((rows, cols))).round(4)
+        w = np.zeros_like(d)
+    if kind not in ("all_nodata", "flat"):
+        d[rng.uniform(size=d.shape) < 0.05] = nodata
+    w[rng.uniform(size=w.shape) < 0.2] = 0
+    D = ascgrid.pad_grid(d.astype(dt), dt(nodata))
+    W = ascgrid.pad_grid(np.where(d > nodata, w, 0).astype(dt), dt(0))
+    return D, W
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("kind", ["flat", "ulp", "tiny", "negative", "all_nodata", "dry"])
+def test_adversarial_inputs_match_oracle(cuda_lib, oracle, dt, kind):
+    """Ties, water at the rounding error of the surface sums, subnormal water, negative elevations, grids
+    without a valid cell, dry grids, single rows and columns - all kernels, all modules, zero threshold 0."""
+    from wdpm_b200 import F32, F64
+    from wdpm_b200.solver import PRODUCTION_FUSED_VARIANT_F64
+    code = F64 if dt == np.float64 else F32
+    rng = np.random.default_rng(500 + ["flat", "ulp", "tiny", "negative", "all_nodata", "dry"].index(kind))
+    variants = [(1, 0), (2, 2), (3, 0)] + ([(2, PRODUCTION_FUSED_VARIANT_F64)] if dt == np.float64 else [(2, 7)])
+    for rows, cols in ((40, 70), (1, 90), (75, 1)):
+        D, W = _adversarial_case(rng, rows, cols, dt, kind)
+        for mod in (0, 1, 2):
+            outlet = oracle.find_outlet(D)
+            if mod == 2 and outlet is None:
+                continue  # no cell with dem > 0: the reference has no outlet either (SURVEY appendix A, quirk 5)
+            a = W.copy()
+            ta = oracle.iterate(a, D, NODATA, mod, 12, outlet=outlet or (0, 0), totaldrain=0.0)
+            for kernel, variant in variants:
+                b, tb, _ = _cuda_iterate(cuda_lib, D, W, mod, dt, 12, outlet=outlet, td=0.0, kernel=kernel, fused_variant=variant)
+                assert np.array_equal(a, b), (kind, rows, cols, mod, kernel, variant, int((a != b).sum()))
+                if mod == 2:
+                    assert dt(ta) == dt(tb), (kind, rows, cols, kernel, variant)
+
+
+def test_drain_without_a_positive_elevation_has_no_outlet(cuda_lib):
+    from wdpm_b200 import F64, Solver
+    from wdpm_b200.solver import WdpmError
+    dem = np.full((20, 30), -3.0)
+    with Solver(20, 30, NODATA, 2, dtype=F64) as s:
+        s.upload(dem, np.full_like(dem, 0.1))
+        with pytest.raises(WdpmError):
+            s.find_outlet()
+        with pytest.raises(WdpmError):
+            s.iterate(1)  # Drain refuses to run without an outlet
+
+
 def _outlet_set(D, rng, twv):
     """Outlets that stress the bookkeeping: neighbours of each other, on strip / chunk borders, on the rim."""
     R, Cc = D.shape[0] - 2, D.shape[1] - 2
