@@ -226,9 +226,11 @@ int wdpm_stripe_band(wdpm_solver *s, int32_t *band_row0, int32_t *band_rows, int
                      int32_t *owned_rows);
 int wdpm_stripe_upload(wdpm_solver *s, const void *dem_band, const void *water_band,
                        int32_t band_row0, int32_t band_rows);
-/* One iteration in two halves, for hosts that drive several in-process stripes in lockstep on
- * one GPU (tests): phase 0 = launch the iteration kernel, phase 1 = push halos to neighbours.
- * wdpm_iterate / wdpm_run_block do wait + compute + push per iteration on their own. */
+/* One iteration without the wait for the neighbours' halos, for hosts that drive several
+ * in-process stripes in lockstep on one GPU (tests): phase 0 = launch the iteration kernel, which
+ * also writes this stripe's halo rows into the neighbours' buffers and raises their flags; phase 1
+ * is accepted and does nothing (the halo push used to be a kernel of its own).
+ * wdpm_iterate / wdpm_run_block do wait + compute/push per iteration on their own. */
 int wdpm_stripe_phase(wdpm_solver *s, int32_t phase);
 
 #ifdef __cplusplus

@@ -310,12 +310,13 @@ __device__ __noinline__ void drain_tile_near_outlets(T* w0, T* w1, T* w2, const 
 }
 
 // ---------------------------------------------------------------------------
-// Row-stripe halo exchange over NVLink (peer stores + arrival flags).
-// After iteration `epoch` a stripe copies, from its freshly written water buffer,
+// Row-stripe halo exchange over NVLink (peer stores + arrival flags), fused into k_fused:
+// in iteration `epoch` a stripe writes, with the bulk stores that write its rows home,
 //   its first HB owned rows  -> the stripe above, as that stripe's rows [P_above, P_above+HB)
 //   its last  HA owned rows  -> the stripe below, as that stripe's rows [-HA, 0)
-// (HA = 3, HB = 6: what one fused iteration reads beyond its owned rows), then
-// publishes `epoch` in the neighbours' arrival flags. Whole device rows are copied.
+// (HA = 3, HB = 6: what one fused iteration reads beyond its owned rows; only the owned columns of
+// each strip travel - the margins never change), and the CTA that finishes last publishes `epoch`
+// in the neighbours' arrival flags. k_halo_wait holds the next launch until both halos are in.
 // ---------------------------------------------------------------------------
 
 constexpr int kHaloAbove = 3;
@@ -324,7 +325,8 @@ constexpr int kHaloBelow = 6;
 struct HaloFlags {
     int from_above;   // epoch of the last halo received from the stripe above
     int from_below;
-    int push_count;   // blocks of the running push kernel that have finished copying
+    int push_count;   // CTAs of the running iteration kernel whose rows for the stripe above have landed
+    int push_count_dn;  // ... for the stripe below
     int error;        // set if a wait gave up
 };
 
@@ -335,31 +337,6 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
 }
 __device__ __forceinline__ void st_release_sys(int* p, int v) {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-__global__ void k_halo_push(const int4* __restrict__ src, int4* __restrict__ dst_above, int4* __restrict__ dst_below,
-                            int row_vecs /* int4 per device row */, int P_self, int P_above, HaloFlags* self_flags,
-                            HaloFlags* flags_above, HaloFlags* flags_below, int epoch) {
-    const long long n_up = dst_above ? (long long)kHaloBelow * row_vecs : 0;
-    const long long n_dn = dst_below ? (long long)kHaloAbove * row_vecs : 0;
-    const int4* src_up = src + (long long)(kPadTop + 0) * row_vecs;
-    int4* dst_up = dst_above + (long long)(kPadTop + P_above) * row_vecs;
-    const int4* src_dn = src + (long long)(kPadTop + P_self - kHaloAbove) * row_vecs;
-    int4* dst_dn = dst_below + (long long)(kPadTop - kHaloAbove) * row_vecs;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_up; i += stride) dst_up[i] = src_up[i];
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_dn; i += stride) dst_dn[i] = src_dn[i];
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int done = atomicAdd(&self_flags->push_count, 1);
-        if (done == (int)gridDim.x - 1) {
-            self_flags->push_count = 0;
-            __threadfence_system();
-            if (flags_above) st_release_sys(&flags_above->from_below, epoch);
-            if (flags_below) st_release_sys(&flags_below->from_above, epoch);
-        }
-    }
 }
 
 // Hold the stream until both neighbours' halos of iteration `epoch` have landed.
@@ -455,6 +432,20 @@ struct FusedParams {
     int total_triples;  // ceil((R+2)/3)
     int launch_parity;  // drain event buffer written by this launch
     DrainState<T> ds;
+    // Row stripes: the halo exchange is part of this kernel. Rows the neighbouring stripes read
+    // (my first kHaloBelow owned rows for the stripe above, my last kHaloAbove for the stripe below)
+    // are written to the neighbour's buffer over NVLink by the same bulk stores that write them home,
+    // and the last of the CTAs that own such rows publishes the iteration number in that neighbour's
+    // arrival flag - for the stripe above that is after the first wave of CTAs, so its halo travels
+    // while the rest of this stripe is still being computed.
+    T* up_out;          // the buffer of the stripe above that takes this iteration's rows (nullptr: none)
+    T* dn_out;
+    int P_self, P_up;   // owned padded rows of this stripe / of the stripe above
+    HaloFlags* self_flags;
+    HaloFlags* up_flags;
+    HaloFlags* dn_flags;
+    int up_ctas, dn_ctas;  // CTAs that own rows exported upwards / downwards (the last of them raises the flag)
+    int epoch;
 };
 
 template <typename CFG, typename T>
@@ -564,7 +555,12 @@ k_fused(const FusedParams<T> p) {
                 const int row = 3 * m + 2 + k;
                 if (!tile.owns_row(row)) continue;
                 const size_t dst = (size_t)(row + kPadTop) * (size_t)p.g.pitch + col0 + CFG::HL;
-                bulk_store(p.w_out + dst, ring_w + (size_t)tile.ring_slot(row) * W + CFG::HL, CFG::TWV * sizeof(T));
+                const T* src = ring_w + (size_t)tile.ring_slot(row) * W + CFG::HL;
+                bulk_store(p.w_out + dst, src, CFG::TWV * sizeof(T));
+                if (p.up_out && row < kHaloBelow)  // ... and into the bottom halo of the stripe above
+                    bulk_store(p.up_out + (size_t)(row + p.P_up + kPadTop) * (size_t)p.g.pitch + col0 + CFG::HL, src, CFG::TWV * sizeof(T));
+                if (p.dn_out && row >= p.P_self - kHaloAbove && row < p.P_self)  // ... the top halo of the stripe below
+                    bulk_store(p.dn_out + (size_t)(row - p.P_self + kPadTop) * (size_t)p.g.pitch + col0 + CFG::HL, src, CFG::TWV * sizeof(T));
                 any = true;
             }
         }
@@ -612,6 +608,23 @@ k_fused(const FusedParams<T> p) {
         if (lead) {
             issue_stores(tile.n_steps - 1);
             bulk_wait_read<0>();
+            const bool exp_up = p.up_flags && 3 * tile.m0 < kHaloBelow;
+            const bool exp_dn = p.dn_flags && 3 * tile.m1 > p.P_self - kHaloAbove && 3 * tile.m0 < p.P_self;
+            if (exp_up || exp_dn) {
+                // my rows have landed, also in the neighbour's memory; the CTA that is last to say so raises the flag
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                __threadfence_system();
+                if (exp_up && atomicAdd(&p.self_flags->push_count, 1) == p.up_ctas - 1) {
+                    p.self_flags->push_count = 0;
+                    __threadfence_system();
+                    st_release_sys(&p.up_flags->from_below, p.epoch);
+                }
+                if (exp_dn && atomicAdd(&p.self_flags->push_count_dn, 1) == p.dn_ctas - 1) {
+                    p.self_flags->push_count_dn = 0;
+                    __threadfence_system();
+                    st_release_sys(&p.dn_flags->from_above, p.epoch);
+                }
+            }
         }
         return;
     }

@@ -253,19 +253,27 @@ int colour_iterations(wdpm_solver* s, int n) {
     return WDPM_OK;
 }
 
-// Copy the rows the neighbours need out of the buffer just written and raise their flags.
-int halo_push(wdpm_solver* s) {
-    s->epoch++;
-    if (!s->above.present && !s->below.present) return WDPM_OK;
-    const int row_vecs = (int)((size_t)s->g.pitch * s->esize / 16);
-    k_halo_push<<<32, 256, 0, s->stream>>>(static_cast<const int4*>(s->w[s->cur]),
-                                           s->above.present ? static_cast<int4*>(s->above.w[s->cur]) : nullptr,
-                                           s->below.present ? static_cast<int4*>(s->below.w[s->cur]) : nullptr, row_vecs, s->P,
-                                           s->above.P, s->flags, s->above.present ? s->above.flags : nullptr,
-                                           s->below.present ? s->below.flags : nullptr, s->epoch);
-    s->launches++;
-    CUDA_TRY(cudaGetLastError());
-    return WDPM_OK;
+// Fill in what the iteration kernel needs to export this iteration's halo rows (kernels.cuh, FusedParams).
+// The neighbours run in lockstep on the buffer index, so their target buffer has my output's index.
+template <typename T>
+void set_halo_export(wdpm_solver* s, FusedParams<T>& p) {
+    const bool up = s->stripe && s->above.present, dn = s->stripe && s->below.present;
+    if (s->stripe) s->epoch++;
+    p.up_out = up ? static_cast<T*>(s->above.w[s->cur ^ 1]) : nullptr;
+    p.dn_out = dn ? static_cast<T*>(s->below.w[s->cur ^ 1]) : nullptr;
+    p.P_self = s->P;
+    p.P_up = s->above.P;
+    p.self_flags = s->flags;
+    p.up_flags = up ? s->above.flags : nullptr;
+    p.dn_flags = dn ? s->below.flags : nullptr;
+    p.up_ctas = p.dn_ctas = 0;
+    for (int c = 0; c < s->n_chunks; c++) {  // the kernel's own test, per chunk of rows (all strips of a chunk agree)
+        const int m0 = c * s->chunk_triples;
+        const int m1 = m0 + s->chunk_triples < s->total_triples ? m0 + s->chunk_triples : s->total_triples;
+        if (up && 3 * m0 < kHaloBelow) p.up_ctas += s->n_strips;
+        if (dn && 3 * m1 > s->P - kHaloAbove && 3 * m0 < s->P) p.dn_ctas += s->n_strips;
+    }
+    p.epoch = s->epoch;
 }
 
 template <typename T>
@@ -290,14 +298,11 @@ int fused_iterations(wdpm_solver* s, int n) {
             k_halo_wait<<<1, 32, 0, s->stream>>>(s->flags, s->above.present, s->below.present, s->epoch);
             s->launches++;
         }
+        set_halo_export<T>(s, p);  // the launch also pushes the halo rows and raises the neighbours' flags
         CUDA_TRY(v.launch[s->module](p, s->n_strips * s->n_chunks, s->stream));
         s->launches++;
         s->cur ^= 1;
         s->launch_parity ^= 1;
-        if (s->stripe) {
-            const int rc = halo_push(s);
-            if (rc) return rc;
-        }
     }
     if (s->module == WDPM_DRAIN && n_launch > 0) {
         k_fold_events<T><<<1, 256, 0, s->stream>>>(drain_state<T>(s), s->launch_parity ^ 1);
@@ -308,7 +313,8 @@ int fused_iterations(wdpm_solver* s, int n) {
     return colour_iterations<T>(s, n - n_launch * v.K);
 }
 
-// The iteration kernel alone (no halo wait, no push): hosts driving in-process stripes in lockstep.
+// The iteration kernel alone (no halo wait; it exports its halo rows itself): hosts driving in-process
+// stripes in lockstep.
 template <typename T>
 int fused_launch_only(wdpm_solver* s) {
     const FusedVariant<T>& v = fused_variants<T>()[s->variant];
@@ -322,6 +328,7 @@ int fused_launch_only(wdpm_solver* s) {
     p.total_triples = s->total_triples;
     p.launch_parity = s->launch_parity;
     p.ds = drain_state<T>(s);
+    set_halo_export<T>(s, p);
     CUDA_TRY(v.launch[s->module](p, s->n_strips * s->n_chunks, s->stream));
     s->launches++;
     s->cur ^= 1;
@@ -1158,7 +1165,7 @@ int wdpm_stripe_phase(wdpm_solver* s, int32_t phase) {
     if (!s->have_dem) return fail(WDPM_E_STATE, "upload first");
     CUDA_TRY(cudaSetDevice(s->device));
     if (phase == 0) return s->dtype == WDPM_F64 ? fused_launch_only<double>(s) : fused_launch_only<float>(s);
-    if (phase == 1) return halo_push(s);
+    if (phase == 1) return WDPM_OK;  // the iteration kernel has already exported the halo rows
     return fail(WDPM_E_ARG, "phase must be 0 or 1");
 }
 
