@@ -461,7 +461,7 @@ constexpr int kOptAddFast = 1;
 // where 24 warps alone could have 80 (measured: scripts/micro/reg_granularity.cu). With this bit the
 // CTA is launched with a whole fourth warp group (4 warps, one of them the data-movement warp, the
 // others exit at once); that group gives its registers back (setmaxnreg.dec to 24) and the compute
-// warps take them (setmaxnreg.inc to 80): 28*72 = 4*24 + 24*80.
+// warps take them (setmaxnreg.inc to 80): 28*72 = 4*24 + 24*80. (16 compute warps: 96 -> 112.)
 constexpr int kOptRegRealloc = 2;
 __host__ __device__ constexpr int fused_extra_threads(int opt) { return (opt & kOptRegRealloc) ? 128 : 32; }
 
@@ -485,7 +485,12 @@ __global__ void __launch_bounds__(NTHREADS + fused_extra_threads(OPT), MINB)
 k_fused(const FusedParams<T> p) {
     constexpr int NALL = NTHREADS + fused_extra_threads(OPT);  // threads of the CTA
     constexpr bool REALLOC = (OPT & kOptRegRealloc) != 0;
-    static_assert(!REALLOC || (NTHREADS == 768 && MINB == 1), "register reallocation is sized for 24 compute warps, one CTA per SM");
+    // launch budget (what ptxas derives from the launch bounds) and what the compute warps can have once the
+    // fourth warp group has shrunk to 24: 768 compute threads -> 72 and 80; 512 -> 96 and 112
+    constexpr int kLaunchRegs = (65536 / NALL) & ~7;
+    constexpr int kComputeRegs = ((kLaunchRegs * NALL - 128 * 24) / NTHREADS) & ~7;
+    static_assert(!REALLOC || (MINB == 1 && NTHREADS % 128 == 0 && kComputeRegs > kLaunchRegs && kComputeRegs <= 232),
+                  "register reallocation needs whole warp groups, one CTA per SM");
     constexpr int W = CFG::W, NT = CFG::NT, NPH = CFG::NPH, NRING = CFG::NRING, NSTAGE = CFG::NSTAGE, PF = CFG::PF;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* ring_w = reinterpret_cast<T*>(smem_raw);
@@ -629,7 +634,7 @@ k_fused(const FusedParams<T> p) {
         return;
     }
 
-    if (REALLOC) asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
+    if (REALLOC) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kComputeRegs));
 
     // Static work assignment: in every sub-step thread `tid` relaxes tiles number tid,
     // tid+NTHREADS, ... of the NPH*NT*NC tiles (phase-major, then triple slot, then column), so its

@@ -19,7 +19,7 @@ namespace {
 
 constexpr int kDefaultVariantF64 = 13;  // 384-column window, two row triples per phase, 24 compute warps at 80 registers, Add fast step
 constexpr int kDefaultVariantF32 = 7;   // 512-column window, two CTAs of 16 compute warps per SM
-constexpr int kDefaultVariantF64Drain = 1;  // Drain's relax step needs more registers than 24 warps leave: 16 warps, 512 columns
+constexpr int kDefaultVariantF64Drain = 14;  // Drain needs ~110 registers: 16 compute warps at 112 (register reallocation), 512 columns
 // Grids of a few hundred thousand cells (the reference's basin5 is 482 x 471) cannot fill 148 SMs
 // with long chunks: narrow windows, two CTAs per SM and chunks of a few row triples spread the
 // rows over the whole chip in one wave (measured on basin5: 18 us per iteration against 37 us for
@@ -111,6 +111,7 @@ const std::vector<FusedVariant<double>>& fused_variants<double>() {
         make_variant<double, MwCfg<384, 2, 1, 1>, 768, 1, kOptAddFast>(),  // 11: as 10, Add with the sign gate and cap-free chains
         make_variant<double, MwCfg<64, 1, 1, 1>, 128, 1, kOptAddFast>(),   // 12: test window with the Add fast path
         make_variant<double, MwCfg<384, 2, 1, 1>, 768, 1, kOptAddFast | kOptRegRealloc>(),  // 13: as 11, compute warps at 80 registers
+        make_variant<double, MwCfg<512, 1, 1, 2>, 512, 1, kOptRegRealloc>(),                // 14: as 1, compute warps at 112 registers
     };
     return v;
 }
