@@ -84,6 +84,37 @@ __global__ void k(double* out, long long* cyc, const double* in, int reps) {
     if (threadIdx.x == 0) cyc[0] = t1 - t0;
 }
 
+template <int MODE>
+__global__ void kf(float* out, long long* cyc, const double* in, int reps) {
+    float w[3][5], d[3][5];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 5; c++) {
+            w[r][c] = (float)in[(threadIdx.x * 31 + r * 3 + c) % 256];
+            d[r][c] = 5.0f + (float)in[(threadIdx.x * 17 + r * 5 + c) % 256];
+        }
+    __syncthreads();
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < reps; i++) {
+        if (MODE == 0) relax_window5<float, kAdd, 0, false>(w, d);
+        if (MODE == 1) {  // the fp64 fast formulation transplanted to fp32: no cap, gate read off h
+            const float dc = d[1][1];
+            float wc = w[1][1];
+#define P32(r, c) push_add_fast<float>(dc, wc, d[r][c], w[r][c])
+            P32(0, 0); P32(0, 1); P32(0, 2); P32(1, 0); P32(1, 2); P32(2, 0); P32(2, 1); P32(2, 2);
+#undef P32
+            w[1][1] = wc;
+        }
+        w[1][1] += 0.3f;
+    }
+    long long t1 = clock64();
+    __syncthreads();
+    float s = 0;
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) s += w[r][c];
+    out[threadIdx.x] = s;
+    if (threadIdx.x == 0) cyc[0] = t1 - t0;
+}
+
 int main() {
     double *o, *in; long long* c;
     cudaMalloc(&o, 1024 * 8); cudaMalloc(&c, 8); cudaMalloc(&in, 256 * 8);
@@ -106,6 +137,18 @@ int main() {
             if (mode == 7) k<7><<<1, threads>>>(o, c, in, reps);
             long long cy; cudaMemcpy(&cy, c, 8, cudaMemcpyDeviceToHost);
             printf("%-36s warps/scheduler %d: %8.1f cycles per rep per warp-slot, %7.2f cycles per rep per scheduler-warp\n", names[mode], wps,
+                   (double)cy / reps, (double)cy / reps / wps);
+        }
+    }
+    const char* fnames[2] = {"fp32 reference step x8 (fminf, predicated adds)", "fp32 no cap, sign gate"};
+    float* of; cudaMalloc(&of, 1024 * 4);
+    for (int mode = 0; mode < 2; mode++) {
+        for (int wps = 1; wps <= 8; wps += (wps < 4 ? 1 : 2)) {
+            const int threads = 128 * wps;
+            if (mode == 0) kf<0><<<1, threads>>>(of, c, in, reps);
+            if (mode == 1) kf<1><<<1, threads>>>(of, c, in, reps);
+            long long cy; cudaMemcpy(&cy, c, 8, cudaMemcpyDeviceToHost);
+            printf("%-48s warps/scheduler %d: %8.1f cycles per rep per warp-slot, %7.2f cycles per rep per scheduler-warp\n", fnames[mode], wps,
                    (double)cy / reps, (double)cy / reps / wps);
         }
     }
