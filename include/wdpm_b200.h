@@ -138,6 +138,19 @@ int wdpm_get_outlet_drains(wdpm_solver *s, double *values, int32_t n);
  * outlet's total and zeroes the others, get returns the sum */
 int wdpm_set_total_drain(wdpm_solver *s, double value);
 int wdpm_get_total_drain(wdpm_solver *s, double *value);
+/* Module chaining. The reference runs Add -> Drain -> Subtract as three processes that hand the
+ * water grid on through "%f" text files (validation/validate_WDPM.sh:77-99). A host that runs the
+ * modules in one process can keep the grids in HBM instead:
+ *   wdpm_copy_state   copies the elevations and/or the current water grid of `src` into `dst` (another
+ *                     solver for the same DEM on the same device, e.g. created for the next module),
+ *                     device to device;
+ *   wdpm_quantize_water applies to every valid cell what the file hand-over does to it - round to 6
+ *                     decimals exactly as fprintf("%f") + fscanf("%lf") do (include/wdpm_quantize.h) -
+ *                     so the next module starts from bit-identical values. */
+#define WDPM_COPY_DEM 1
+#define WDPM_COPY_WATER 2
+int wdpm_copy_state(wdpm_solver *dst, wdpm_solver *src, int32_t what);
+int wdpm_quantize_water(wdpm_solver *s);
 /* water depth at one cell (for totaldrain = max(bigwater[outlet],0), src/WDPMCL.c:1029) */
 int wdpm_get_cell_water(wdpm_solver *s, int32_t row, int32_t col, double *value);
 

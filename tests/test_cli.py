@@ -70,6 +70,39 @@ def test_validation_sequence_through_the_binary(host_bin, tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("gpus", ["1", "2"])
+def test_chained_modules_write_the_same_files_as_separate_runs(host_bin, tmp_path, gpus):
+    """`wdpmcl_b200 chain`: Add -> Drain -> Subtract in one process, grids handed on in HBM (one GPU) or in
+    host memory (stripes) with the "%f" quantisation a file gives: every output file and report must equal
+    the unmodified reference's, exactly as for three separate runs."""
+    import os
+    from test_oracle import _check_goldens
+    dem = gunzip_to("basin5.asc.gz", tmp_path / "basin5.asc")
+    add, drain, sub = tmp_path / "add.asc", tmp_path / "drain.asc", tmp_path / "sub.asc"
+    pfs = []
+    for name, body in (("add10", f"add {dem} NULL {add} NULL 10 1.0 1.0 1 1 0.005 0"),
+                       ("drain", f"drain {dem} {add} {drain} NULL 0.1 1.0 1 1 0.005 0"),
+                       ("sub10", f"subtract {dem} {drain} {sub} NULL 10 1.0 1 1 0.005 0")):
+        pf = tmp_path / f"{name}.txt"
+        pf.write_text(body + "\n")
+        pfs.append(str(pf))
+    res = subprocess.run([str(host_bin), "chain"] + pfs, capture_output=True, text=True, timeout=900,
+                         env=dict(os.environ, WDPM_B200_GPUS=gpus))
+    assert res.returncode == 0, res.stdout[-800:] + res.stderr
+    for name, out in (("add10", add), ("drain", drain), ("sub10", sub)):
+        text = out.read_text()
+        assert text == golden_text(f"ref_opencl_{name}.asc.gz"), name
+        _check_goldens(name, text)
+    # the chained stdout is the three reports one after the other
+    reports = res.stdout.split("WDPM run summary")
+    assert len(reports) == 4
+    want = []
+    for name in ("add10", "drain", "sub10"):
+        want += _normalise((GOLDEN / f"ref_opencl_{name}.txt").read_text())
+    assert [ln for ln in _normalise(res.stdout) if ln] == [ln for ln in want if ln]  # blank lines at the seams aside
+
+
+@pytest.mark.gpu
 def test_parameter_file_and_scratch_resume(host_bin, tmp_path):
     """Parameter-file form (WDPMCL.c:334-342) with an iteration limit and a scratch file, then a resume
     from that scratch file: the two-leg run must end where the uninterrupted run ends."""

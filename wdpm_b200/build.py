@@ -16,7 +16,7 @@ LIB = PKG / "libwdpm_b200.so"
 HOST_BIN = PKG / "host" / "wdpmcl_b200"
 SOURCES = [PKG / "csrc" / "solver.cu"]
 HEADERS = [PKG / "csrc" / "kernels.cuh", PKG / "csrc" / "relax.cuh", PKG / "csrc" / "mw_schedule.h",
-           ROOT / "include" / "wdpm_b200.h"]
+           ROOT / "include" / "wdpm_b200.h", ROOT / "include" / "wdpm_quantize.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -58,7 +58,7 @@ def build_host(force: bool = False) -> Path | None:
     src = PKG / "host" / "wdpm_host.c"
     if not src.exists():
         return None
-    if force or _stale(HOST_BIN, [src, ROOT / "include" / "wdpm_b200.h", LIB]):
+    if force or _stale(HOST_BIN, [src, ROOT / "include" / "wdpm_b200.h", ROOT / "include" / "wdpm_quantize.h", LIB]):
         cmd = ["/usr/bin/gcc", "-O2", "-std=c11", "-fopenmp", "-Wall", "-Wextra", "-I", str(ROOT / "include"), str(src), "-o", str(HOST_BIN),
                "-L", str(PKG), "-lwdpm_b200", "-Wl,-rpath,$ORIGIN/..", "-lm", "-lpthread"]
         res = subprocess.run(cmd, capture_output=True, text=True)

@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
+#include "../../include/wdpm_quantize.h"
 #include "mw_schedule.h"
 #include "relax.cuh"
 
@@ -76,6 +77,15 @@ __global__ void k_apply_subtract(T* __restrict__ w, const T* __restrict__ d, lon
             w[a] = (v > T(0)) ? v : T(0);
         }
     }
+}
+
+// What writing the water grid with "%f" and reading it back does to every valid cell
+// (include/wdpm_quantize.h): lets chained modules keep the grid in HBM and still start from the
+// values the reference's file hand-over gives them.
+template <typename T>
+__global__ void k_quantize_water(T* __restrict__ w, const T* __restrict__ d, long long n) {
+    for (long long a = blockIdx.x * (long long)blockDim.x + threadIdx.x; a < n; a += (long long)gridDim.x * blockDim.x)
+        if (is_valid_elevation(d[a])) w[a] = (T)wdpm_quantize6((double)w[a]);
 }
 
 // Block prologue (src/WDPMCL.c:1055-1073): w < thres -> 0 over the whole padded

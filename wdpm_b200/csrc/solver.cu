@@ -945,6 +945,59 @@ int wdpm_get_total_drain(wdpm_solver* s, double* value) {
     return WDPM_OK;
 }
 
+int wdpm_quantize_water(wdpm_solver* s) {
+    if (!s) return fail(WDPM_E_ARG, "null solver");
+    if (!s->have_dem) return fail(WDPM_E_STATE, "upload first");
+    if (s->in_block) return fail(WDPM_E_STATE, "a block is open");
+    CUDA_TRY(cudaSetDevice(s->device));
+    const long long n = s->g.cells_dev();
+    const int grid = grid_for(n, 256, s->sm_count);
+    if (s->dtype == WDPM_F64) k_quantize_water<double><<<grid, 256, 0, s->stream>>>(static_cast<double*>(s->w[s->cur]), static_cast<const double*>(s->dem), n);
+    else k_quantize_water<float><<<grid, 256, 0, s->stream>>>(static_cast<float*>(s->w[s->cur]), static_cast<const float*>(s->dem), n);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return WDPM_OK;
+}
+
+int wdpm_copy_state(wdpm_solver* dst, wdpm_solver* src, int32_t what) {
+    if (!dst || !src) return fail(WDPM_E_ARG, "null solver");
+    if (dst == src || !(what & (WDPM_COPY_DEM | WDPM_COPY_WATER))) return fail(WDPM_E_ARG, "nothing to copy");
+    if (dst->stripe || src->stripe) return fail(WDPM_E_UNSUPPORTED, "stripe solvers take their grids from the host");
+    if (dst->device != src->device || dst->dtype != src->dtype || dst->cfg.rows != src->cfg.rows || dst->g.C != src->g.C)
+        return fail(WDPM_E_ARG, "solvers differ in device, precision or grid size");
+    if (!src->have_dem) return fail(WDPM_E_STATE, "the source solver holds no grids");
+    if (!(what & WDPM_COPY_DEM) && !dst->have_dem) return fail(WDPM_E_STATE, "the destination needs elevations first");
+    if (dst->in_block || src->in_block) return fail(WDPM_E_STATE, "a block is open");
+    CUDA_TRY(cudaSetDevice(dst->device));
+    // the padded grid (halo ring included) sits at the same offset in both layouts; the pitches may differ
+    const size_t off_d = ((size_t)kPadTop * dst->g.pitch + kPadLeft) * dst->esize, off_s = ((size_t)kPadTop * src->g.pitch + kPadLeft) * src->esize;
+    const size_t width = (size_t)(src->g.C + 2) * src->esize, height = (size_t)(src->g.R + 2);
+    if (what & WDPM_COPY_DEM) {
+        int rc = apply_outlet_marks(src, false);  // the true elevations travel, not the source's outlet marks
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(src->stream));
+        CUDA_TRY(cudaMemcpy2DAsync(static_cast<char*>(dst->dem) + off_d, (size_t)dst->g.pitch * dst->esize, static_cast<const char*>(src->dem) + off_s,
+                                   (size_t)src->g.pitch * src->esize, width, height, cudaMemcpyDeviceToDevice, dst->stream));
+        CUDA_TRY(cudaStreamSynchronize(dst->stream));
+        rc = apply_outlet_marks(src, true);
+        if (rc) return rc;
+        dst->have_dem = true;
+        dst->marks_applied = false;
+        rc = apply_outlet_marks(dst, true);
+        if (rc) return rc;
+    }
+    if (what & WDPM_COPY_WATER) {
+        CUDA_TRY(cudaStreamSynchronize(src->stream));
+        CUDA_TRY(cudaMemcpy2DAsync(static_cast<char*>(dst->w[dst->cur]) + off_d, (size_t)dst->g.pitch * dst->esize,
+                                   static_cast<const char*>(src->w[src->cur]) + off_s, (size_t)src->g.pitch * src->esize, width, height,
+                                   cudaMemcpyDeviceToDevice, dst->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(dst->stream));
+    CUDA_TRY(cudaStreamSynchronize(src->stream));
+    return WDPM_OK;
+}
+
 int wdpm_get_cell_water(wdpm_solver* s, int32_t row, int32_t col, double* value) {
     if (!s || !value) return fail(WDPM_E_ARG, "null argument");
     row -= s->G;

@@ -16,6 +16,14 @@
  * The update schedule is the OpenCL branch's (runoff.cl arithmetic); see DESIGN.md
  * for how that differs from the serial branch in the last bits of Drain/Subtract.
  *
+ * Extension: `wdpmcl_b200 chain paramfile1 paramfile2 ...` runs several modules in ONE process (the
+ * reference's validate_WDPM.sh:77-99 runs Add -> Drain -> Subtract as three). Each module prints its
+ * usual report and writes its usual files; what is saved is the hand-over: a DEM named again is not
+ * parsed again, and a water file that is the previous module's output is not read back - on one GPU
+ * the grids go from solver to solver inside HBM (wdpm_copy_state) and the water gets the "%f"
+ * quantisation a file would have given it (wdpm_quantize_water; include/wdpm_quantize.h), so every
+ * output is byte-identical to what the separate runs write (tests/test_cli.py).
+ *
  * Environment: WDPM_B200_DEVICE (first CUDA ordinal, default 0), WDPM_B200_KERNEL
  * (0 auto, 1 colour, 2 fused, 3 resident), WDPM_B200_GPUS (number of GPUs, default 1:
  * the DEM is cut into that many row stripes, one solver per GPU, halos exchanged over
@@ -36,6 +44,7 @@
 #endif
 
 #include "wdpm_b200.h"
+#include "wdpm_quantize.h"
 
 enum { BLOCK_ITERATIONS = 1000 }; /* IterationNum, WDPMCL.c:597 */
 enum { EXIT_USAGE = 42 };
@@ -544,6 +553,20 @@ static void mark_nodata(double *w, const double *dem, size_t n, double nodata)
         if (dem[k] <= nodata) w[k] = nodata;
 }
 
+/* What a chained run carries from one module to the next (all of it owned here). */
+typedef struct {
+    int active;
+    char dem_path[512];
+    asc_header hdr;
+    double *dem;
+    char out_path[512];
+    double *water;        /* the previous module's output as a file would give it back: "%f"-quantised */
+    solver_set prev;      /* the previous module's solver(s), grids still in HBM */
+    int have_prev;
+} chain_state;
+
+static int run_module(int ntok, char tok[][512], int argc, chain_state *cs);
+
 int main(int argc, char **argv)
 {
     setbuf(stdout, NULL);
@@ -561,6 +584,24 @@ int main(int argc, char **argv)
         double *g0 = read_grid(argv[2], h0.nrows, h0.ncols, 0.0, NULL);
         return (g0 && write_grid(argv[3], &h0, g0) == 0) ? 0 : 1;
     }
+    if (argc >= 3 && !strcmp(argv[1], "chain")) { /* extension: several parameter files, one process */
+        static chain_state cs;
+        cs.active = 1;
+        for (int f = 2; f < argc; f++) {
+            ntok = tokens_from_file(argv[f], tok, 16);
+            if (ntok < 1) {
+                perror("Couldn't read the parameter file");
+                return 1;
+            }
+            const int rc = run_module(ntok, tok, 2, &cs);
+            if (rc != 0) return rc;
+        }
+        if (cs.have_prev)
+            for (int g = 0; g < cs.prev.n; g++) wdpm_destroy(cs.prev.sv[g]);
+        free(cs.dem);
+        free(cs.water);
+        return 0;
+    }
     if (argc == 2) {
         if (is_module(argv[1])) {
             usage_module(argv[1]);
@@ -577,7 +618,12 @@ int main(int argc, char **argv)
         usage_module(argv[1]);
         return EXIT_USAGE;
     }
+    return run_module(ntok, tok, argc, NULL);
+}
 
+/* One module, start to finish (the body of the reference's main, WDPMCL.c:308-1486). */
+static int run_module(int ntok, char tok[][512], int argc, chain_state *cs)
+{
     banner(tok[0]);
     run_args a;
     if (fill_args(&a, ntok, tok) != 0 || (argc > 2 && argc != (!strcmp(tok[0], "add") ? 13 : 12))) {
@@ -591,14 +637,19 @@ int main(int argc, char **argv)
     const double depth = is_add ? a.depth_mm / 1000.0 : a.depth_mm / 1000;
     const double thres = a.thres_mm / 1000;
 
-    /* DEM header and data */
-    char *hb = slurp(a.dem, NULL);
+    /* DEM header and data (a chained run keeps the DEM it parsed for the module before) */
+    const int same_dem = cs && cs->dem && !strcmp(cs->dem_path, a.dem);
     asc_header hdr;
-    if (!hb || !parse_header(hb, &hdr)) {
-        perror("Couldn't read the DEM file");
-        return 1;
+    if (same_dem) {
+        hdr = cs->hdr;
+    } else {
+        char *hb = slurp(a.dem, NULL);
+        if (!hb || !parse_header(hb, &hdr)) {
+            perror("Couldn't read the DEM file");
+            return 1;
+        }
+        free(hb);
     }
-    free(hb);
     line("                  ");
     printf("%30s\n", "ArcGIS file header");
     printf("%30s %d\n", hdr.name[0], hdr.ncols);
@@ -608,10 +659,22 @@ int main(int argc, char **argv)
     const size_t n = (size_t)rows * (size_t)cols;
     const double nodata = hdr.nodata, cellarea = hdr.cellsize * hdr.cellsize;
     printf("%30s\n", "Setting array sizes");
-    double *dem = read_grid(a.dem, rows, cols, 0.0, NULL);
+    double *dem = same_dem ? cs->dem : read_grid(a.dem, rows, cols, 0.0, NULL);
     if (!dem) {
         perror("Couldn't read the DEM file");
         return 1;
+    }
+    if (cs && !same_dem) { /* a new DEM: whatever the chain carried belongs to the old one */
+        free(cs->dem);
+        free(cs->water);
+        cs->water = NULL;
+        cs->out_path[0] = 0;
+        if (cs->have_prev)
+            for (int g = 0; g < cs->prev.n; g++) wdpm_destroy(cs->prev.sv[g]);
+        cs->have_prev = 0;
+        cs->dem = dem;
+        cs->hdr = hdr;
+        snprintf(cs->dem_path, sizeof cs->dem_path, "%s", a.dem);
     }
     line("           ");
     line("           ");
@@ -621,7 +684,7 @@ int main(int argc, char **argv)
 
     /* water: scratch file (resume) > water file > zeros; the messages follow WDPMCL.c:666-989 */
     double *water = NULL;
-    int resumed = 0;
+    int resumed = 0, chained = 0; /* chained: the water file is the output the module before has just written */
     double initial_vol = 0.0;
     if (!is_null_name(a.scratch)) {
         if (file_exists(a.scratch)) {
@@ -643,7 +706,13 @@ int main(int argc, char **argv)
         const int named = is_drain || !is_null_name(a.water);
         if (named && file_exists(a.water)) {
             printf("%30s\n", "Existing water file found");
-            water = read_grid(a.water, rows, cols, 0.0, NULL);
+            if (cs && cs->water && !strcmp(cs->out_path, a.water)) {
+                water = cs->water; /* what reading that file back would give */
+                cs->water = NULL;
+                chained = 1;
+            } else {
+                water = read_grid(a.water, rows, cols, 0.0, NULL);
+            }
             if (!is_drain && !is_null_name(a.scratch)) { /* only this path recomputes the initial volume (:690-699, :846-855) */
                 for (size_t k = 0; k < n; k++)
                     if (is_add ? dem[k] > nodata : dem[k] > 0) initial_vol += water[k];
@@ -680,9 +749,23 @@ int main(int argc, char **argv)
     cfg.zero_threshold = thres;
     cfg.device = getenv("WDPM_B200_DEVICE") ? atoi(getenv("WDPM_B200_DEVICE")) : 0;
     cfg.kernel = getenv("WDPM_B200_KERNEL") ? atoi(getenv("WDPM_B200_KERNEL")) : WDPM_KERNEL_AUTO;
-    static solver_set ss;
+    solver_set ss;
     set_create(&ss, cfg, getenv("WDPM_B200_GPUS") ? atoi(getenv("WDPM_B200_GPUS")) : 1);
-    set_upload(&ss, dem, water, cols);
+    if (cs && cs->have_prev && same_dem && ss.n == 1 && cs->prev.n == 1) {
+        /* same DEM, one GPU: the grids never leave HBM */
+        if (wdpm_copy_state(ss.sv[0], cs->prev.sv[0], WDPM_COPY_DEM | (chained ? WDPM_COPY_WATER : 0)) != WDPM_OK) die_solver("hand the grids on");
+        if (chained) {
+            if (wdpm_quantize_water(ss.sv[0]) != WDPM_OK) die_solver("quantise the water grid");
+        } else if (wdpm_upload_water(ss.sv[0], water) != WDPM_OK) {
+            die_solver("upload the water grid");
+        }
+    } else {
+        set_upload(&ss, dem, water, cols);
+    }
+    if (cs && cs->have_prev) {
+        for (int g = 0; g < cs->prev.n; g++) wdpm_destroy(cs->prev.sv[g]);
+        cs->have_prev = 0;
+    }
     if (!resumed) {
         for (int g = 0; g < ss.n; g++) {
             if (is_add && wdpm_apply_add(ss.sv[g], depth, a.runoff_frac) != WDPM_OK) die_solver("add water");
@@ -730,7 +813,8 @@ int main(int argc, char **argv)
     struct timeval t0;
     gettimeofday(&t0, NULL);
     int k = 0, done = 0;
-    static scratch_writer scratch;
+    scratch_writer scratch;
+    memset(&scratch, 0, sizeof scratch);
     while (!done) {
         const double old_drain = total_drain;
         wdpm_block_result r;
@@ -792,6 +876,17 @@ int main(int argc, char **argv)
         return 1;
     }
     printf("%20s %10.2f %s\n", "Run Time", seconds_since(&t0), "s");
+    free(scratch.grid);
+    if (cs) { /* keep what the next module may want: the solver (grids in HBM) and the output as its file reads back */
+        cs->prev = ss;
+        cs->have_prev = 1;
+#pragma omp parallel for schedule(static)
+        for (long long i = 0; i < (long long)n; i++) water[i] = wdpm_quantize6(water[i]);
+        free(cs->water);
+        cs->water = water;
+        snprintf(cs->out_path, sizeof cs->out_path, "%s", a.output);
+        return 0;
+    }
     for (int g = 0; g < ss.n; g++) wdpm_destroy(ss.sv[g]);
     free(dem);
     free(water);

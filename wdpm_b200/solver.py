@@ -198,6 +198,14 @@ class Solver:
         _check(self._lib.wdpm_get_outlet_drains(self._h, out.ctypes.data_as(C.POINTER(C.c_double)), C.c_int32(n)))
         return out
 
+    def quantize_water(self):
+        """What a "%f" file hand-over does to the water grid (module chaining; include/wdpm_quantize.h)."""
+        _check(self._lib.wdpm_quantize_water(self._h))
+
+    def copy_state_from(self, src: "Solver", dem: bool = True, water: bool = True):
+        """Take the elevations and/or the current water grid of another solver of the same DEM, inside HBM."""
+        _check(self._lib.wdpm_copy_state(self._h, src._h, C.c_int32((1 if dem else 0) | (2 if water else 0))))
+
     def set_total_drain(self, v: float):
         _check(self._lib.wdpm_set_total_drain(self._h, C.c_double(v)))
 
