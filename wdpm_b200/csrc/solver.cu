@@ -18,7 +18,7 @@ using namespace wdpm;
 namespace {
 
 constexpr int kDefaultVariantF64 = 13;  // 384-column window, two row triples per phase, 24 compute warps at 80 registers, Add fast step
-constexpr int kDefaultVariantF32 = 7;   // 512-column window, two CTAs of 16 compute warps per SM
+constexpr int kDefaultVariantF32 = 12;  // 484-column window (160 tiles = 5 whole warps per row group, named barriers), two CTAs of 15 compute warps per SM
 constexpr int kDefaultVariantF64Drain = 14;  // Drain needs ~110 registers: 16 compute warps at 112 (register reallocation), 512 columns
 // Grids of a few hundred thousand cells (the reference's basin5 is 482 x 471) cannot fill 148 SMs
 // with long chunks: narrow windows, two CTAs per SM and chunks of a few row triples spread the
