@@ -73,5 +73,46 @@ static long long run(long long n, unsigned long long seed, long long* n_cap_bite
     return bad;
 }
 
+// Drain: push<T, kDrain> (reference form) against push_drain_fast<T> (gate and max(flow,0) folded into the
+// factor) on chains without -0.0 water - the condition under which the solver selects the fast form.
+template <typename T>
+static long long run_drain(long long n, unsigned long long seed) {
+    std::mt19937_64 rng(seed);
+    std::uniform_real_distribution<double> U(0.0, 1.0);
+    long long bad = 0;
+    const T S = invalid_elevation<T>();
+    const double emin = sizeof(T) == 8 ? -330.0 : -46.0;
+    for (long long it = 0; it < n; it++) {
+        const int mode = (int)(rng() % 6);
+        double base = 500.0, relief = 3.0;
+        if (mode == 1) relief = 1e-9;
+        if (mode == 2) { base = 0.0; relief = 1e-3; }
+        if (mode == 3) { base = -50.0; relief = 10.0; }
+        if (mode == 4) relief = 0.0;
+        if (mode == 5) relief = sizeof(T) == 8 ? 1e-13 : 1e-4;
+        const T dc = (T)(base + relief * (U(rng) - 0.5));
+        T wc = (T)(std::pow(10.0, emin * U(rng) * (rng() % 3 == 0 ? 1.0 : 0.05)) * U(rng));
+        if (rng() % 5 == 0) { const T a = dc < 0 ? -dc : dc; wc = (T)((std::nextafter(a, S) - a) * (0.25 + 1.5 * U(rng))); }
+        if (!(wc > (T)0)) continue;
+        T a_c = wc, b_c = wc;
+        bool ok = true;
+        for (int k = 0; k < 8; k++) {
+            T dn = (T)(base + relief * (U(rng) - 0.5));
+            if (rng() % 9 == 0) dn = S;   // masked neighbour (the sentinel the solver stores)
+            if (rng() % 7 == 0) dn = dc;
+            if (rng() % 7 == 0) dn = std::nextafter(dc, rng() % 2 ? S : -S);
+            T wn = (rng() % 4 == 0) ? (T)0 : (T)(std::pow(10.0, emin * U(rng) * (rng() % 3 == 0 ? 1.0 : 0.05)) * U(rng) * (rng() % 4 == 0 ? 1000.0 : 1.0));
+            T a_n = wn, b_n = wn;
+            push<T, kDrain>(dc, a_c, dn, a_n);
+            push_drain_fast<T>(dc, b_c, dn, b_n);
+            ok = ok && same_bits(a_n, b_n);
+        }
+        ok = ok && same_bits(a_c, b_c);
+        if (!ok) bad++;
+    }
+    return bad;
+}
+extern "C" long long relax_equiv_drain_f64(long long n, unsigned long long seed) { return run_drain<double>(n, seed); }
+
 extern "C" long long relax_equiv_run_f64(long long n, unsigned long long seed, long long* n_cap_bites) { return run<double>(n, seed, n_cap_bites); }
 extern "C" long long relax_equiv_run_f32(long long n, unsigned long long seed, long long* n_cap_bites) { return run<float>(n, seed, n_cap_bites); }

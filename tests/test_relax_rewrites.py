@@ -28,3 +28,11 @@ def test_add_fast_step_is_bit_exact_and_the_cap_never_bites(sfx):
     bad = fn(C.c_longlong(3_000_000), C.c_ulonglong(12345), C.byref(bites))
     assert bad == 0
     assert bites.value == 0  # mini(flow, wc) is a no-op in runoffadd (proof in relax.cuh)
+
+
+def test_drain_fast_step_is_bit_exact_without_negative_zero_water():
+    """push_drain_fast (gate and max(flow,0) folded into the factor) against the reference form; the solver
+    uses it only with a zero threshold > 0, i.e. when no water value is -0.0."""
+    fn = _build().relax_equiv_drain_f64
+    fn.restype = C.c_longlong
+    assert fn(C.c_longlong(3_000_000), C.c_ulonglong(777)) == 0

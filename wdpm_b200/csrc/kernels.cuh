@@ -473,6 +473,10 @@ constexpr int kOptAddFast = 1;
 // others exit at once); that group gives its registers back (setmaxnreg.dec to 24) and the compute
 // warps take them (setmaxnreg.inc to 80): 28*72 = 4*24 + 24*80. (16 compute warps: 96 -> 112.)
 constexpr int kOptRegRealloc = 2;
+// OPT bit 2 (fp64 Drain only): gate and max(flow,0) folded into the scaling factor (relax.cuh,
+// push_drain_fast) - 31 instead of 34 issue cycles per neighbour. Valid when water is never -0.0, which a
+// zero threshold > 0 guarantees; the solver picks the variant accordingly.
+constexpr int kOptDrainFast = 4;
 __host__ __device__ constexpr int fused_extra_threads(int opt) { return (opt & kOptRegRealloc) ? 128 : 32; }
 
 #ifdef WDPM_TIMELINE
@@ -665,7 +669,7 @@ k_fused(const FusedParams<T> p) {
         it_mrel[k] = t - ph * CFG::LAG;
     }
 
-    constexpr bool ADD_FAST = (OPT & kOptAddFast) && MODULE == kAdd && sizeof(T) == 8;
+    constexpr bool ADD_FAST = sizeof(T) == 8 && (((OPT & kOptAddFast) && MODULE == kAdd) || ((OPT & kOptDrainFast) && MODULE == kDrain));  // relax_window5's FAST
 
     // Per tile: the three ring rows it spans this step, and a register window that slides one
     // column per colour sub-pass. wt = 3x3 water (rows x cols jb-1+cofs .. jb+1+cofs), dd = the

@@ -201,6 +201,38 @@ WDPM_HD void push_add_fast(T dc, T& wc, T dn, T& wn) {
     move_if(sign_clear(h), wc, wn, x * T(0.125));  // dc > sn implies h > 0: the gate can be read off h
 }
 
+// Drain, fp64: runoffdrain's step (runoff.cl:112-127) with its gate `if (h > 0)` and its clamp
+// maxi(flow, 0) folded into the scaling factor, as in push_add_fast: give = x * (h > 0 && x >= +0 ?
+// 0.125 : +0.0). A closed gate or a clamped flow then moves -0.0 or +0.0, where the reference moves
+// nothing or +0.0 - the same bits unless the neighbour's water is -0.0. The solver selects this form
+// only when its zero threshold is > 0: the block prologue (WDPMCL.c:1055-1065) then turns any -0.0
+// from a water file into +0.0 before the first iteration, and no step can produce one (x - x = +0,
+// +0 + -0 = +0). The cap mini(flow, wc) stays: the four-term flow can exceed a tiny wc.
+template <typename T>
+WDPM_HD void push_drain_fast(T dc, T& wc, T dn, T& wn) {
+    if (sizeof(T) != 8) {  // fp32 keeps the reference form (predicated adds)
+        push<T, kDrain>(dc, wc, dn, wn);
+        return;
+    }
+    const double sn = (double)dn + (double)wn;
+    const double sc = (double)dc + (double)wc;
+    const double h = sc - sn;
+    const bool pos = h > 0.0;
+    const double x = ((double)dc > sn) ? (double)wc : (((double)dc - (double)dn) + ((double)wc - (double)wn));
+#ifdef __CUDA_ARCH__
+    int mhi;  // factor = (pos && x's sign bit clear) ? 0.125 : +0.0; only its high word is selected
+    asm("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %2, 0;\n\tsetp.ge.and.s32 p, %1, 0, q;\n\tselp.b32 %0, 0x3fc00000, 0, p;\n\t}"
+        : "=r"(mhi) : "r"(__double2hiint(x)), "r"((int)pos));
+    const double m = __hiloint2double(mhi, 0);
+#else
+    const double m = (pos && sign_clear(x)) ? 0.125 : 0.0;
+#endif
+    double flow = x * m;
+    flow = (flow <= (double)wc) ? flow : (double)wc;  // mini, as the reference writes it
+    wc = (T)((double)wc - flow);
+    wn = (T)((double)wn + flow);
+}
+
 // The eight steps on a register window that "slides" one column per colour sub-pass: w and d hold the
 // tile's water / elevations over ALL three positions (3x5); sub-pass COFS works on columns
 // COFS..COFS+2. Indices are compile-time constants, so the slide is register renaming - no moves.
@@ -211,6 +243,7 @@ WDPM_HD void relax_window5(T (&w)[3][5], const T (&d)[3][5]) {
 #define WDPM_PUSH5(r, c)                                                                     \
     do {                                                                                     \
         if (FAST && MODULE == kAdd && sizeof(T) == 8) push_add_fast<T>(dc, wc, d[r][COFS + c], w[r][COFS + c]); \
+        else if (FAST && MODULE == kDrain && sizeof(T) == 8) push_drain_fast<T>(dc, wc, d[r][COFS + c], w[r][COFS + c]); \
         else push<T, MODULE>(dc, wc, d[r][COFS + c], w[r][COFS + c]);                        \
     } while (0)
     WDPM_PUSH5(0, 0); WDPM_PUSH5(0, 1); WDPM_PUSH5(0, 2);

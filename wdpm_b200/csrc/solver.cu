@@ -19,6 +19,7 @@ namespace {
 
 constexpr int kDefaultVariantF64 = 13;  // 384-column window, two row triples per phase, 24 compute warps at 80 registers, Add fast step
 constexpr int kDefaultVariantF32 = 12;  // 484-column window (160 tiles = 5 whole warps per row group, named barriers), two CTAs of 15 compute warps per SM
+constexpr int kDefaultVariantF64DrainFast = 15;  // ... with the folded-gate Drain step (zero threshold > 0)
 constexpr int kDefaultVariantF64Drain = 14;  // Drain needs ~110 registers: 16 compute warps at 112 (register reallocation), 512 columns
 // Grids of a few hundred thousand cells (the reference's basin5 is 482 x 471) cannot fill 148 SMs
 // with long chunks: narrow windows, two CTAs per SM and chunks of a few row triples spread the
@@ -112,6 +113,8 @@ const std::vector<FusedVariant<double>>& fused_variants<double>() {
         make_variant<double, MwCfg<64, 1, 1, 1>, 128, 1, kOptAddFast>(),   // 12: test window with the Add fast path
         make_variant<double, MwCfg<384, 2, 1, 1>, 768, 1, kOptAddFast | kOptRegRealloc>(),  // 13: as 11, compute warps at 80 registers
         make_variant<double, MwCfg<512, 1, 1, 2>, 512, 1, kOptRegRealloc>(),                // 14: as 1, compute warps at 112 registers
+        make_variant<double, MwCfg<512, 1, 1, 2>, 512, 1, kOptRegRealloc | kOptDrainFast>(), // 15: as 14, Drain with the gate folded into the factor
+        make_variant<double, MwCfg<64, 1, 1, 1>, 128, 1, kOptDrainFast>(),                  // 16: test window for 15
     };
     return v;
 }
@@ -605,6 +608,8 @@ int wdpm_create(const wdpm_config* cfg, wdpm_solver** out) {
     if (variant < 0 || variant > nvar) { delete s; return fail(WDPM_E_ARG, "fused_variant out of range"); }
     if (variant == 0) {
         variant = s->dtype == WDPM_F64 ? (cfg->module == WDPM_DRAIN ? kDefaultVariantF64Drain : kDefaultVariantF64) : kDefaultVariantF32;
+        // Drain's folded-gate step needs water that is never -0.0: guaranteed by a zero threshold > 0 (relax.cuh)
+        if (s->dtype == WDPM_F64 && cfg->module == WDPM_DRAIN && cfg->zero_threshold > 0.0) variant = kDefaultVariantF64DrainFast;
         if (cells < kSmallGridCells && !is_stripe) variant = s->dtype == WDPM_F64 ? kSmallGridVariantF64 : kSmallGridVariantF32;
         if (cfg->iters_per_launch > 1) {
             variant = 0;
