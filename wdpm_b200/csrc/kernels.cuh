@@ -677,7 +677,7 @@ k_fused(const FusedParams<T> p) {
     // the window is written to shared memory (the left-hand tile needs it next) and only the
     // column that enters is read (the right-hand tile has just published it); after the third
     // sub-pass the whole window is written back.
-    bool run[IPT], slow[IPT], dirty[IPT];
+    bool run[IPT], slow[IPT];
     int row0[IPT];
     T* wrow[IPT][3];
     T wt[IPT][3][5], dd[IPT][3][5];  // wt: columns COFS..COFS+2 are live in sub-pass COFS
@@ -718,7 +718,6 @@ k_fused(const FusedParams<T> p) {
         prepare(s);
 #pragma unroll
         for (int k = 0; k < IPT; k++) {
-            dirty[k] = false;
             if (run[k] && !slow[k]) {
                 const int jl = it_col[k] - 1;
 #pragma unroll
@@ -752,11 +751,8 @@ k_fused(const FusedParams<T> p) {
                     for (int r = 0; r < 3; r++) wt[k][r][COFS + 2] = wrow[k][r][j + 1];
                 }
                 const bool active = run[k] && (wt[k][1][COFS + 1] > T(0)) && is_valid_elevation(dd[k][1][COFS + 1]);
-                if (active) {
-                    relax_window5<T, MODULE, COFS, ADD_FAST>(wt[k], dd[k]);
-                    dirty[k] = true;
-                }
-                if (dirty[k]) {
+                if (active) relax_window5<T, MODULE, COFS, ADD_FAST>(wt[k], dd[k]);
+                if (run[k]) {  // an untouched tile writes back what it read: harmless, and cheaper than keeping track
                     if (COFS < 2) {
 #pragma unroll
                         for (int r = 0; r < 3; r++) wrow[k][r][j - 1] = wt[k][r][COFS];
