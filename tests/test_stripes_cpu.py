@@ -65,10 +65,18 @@ def _worker(rank, world, port, rows, cols, module, n_iters, seed, out_q):
     band_d = D[lo:hi].copy()
     band_w = W[lo:hi].copy()
     outlet = o.find_outlet(D) or (1, 1)
+    # module 3 = Drain with an outlet SET (extension): outlets on and next to the stripe borders and the rim
+    border = plan[1].row0
+    outlet_set = [rc for rc in [outlet, (border, 5), (border - 1, 6), (border + 1, 20), (1, 1), (rows, cols), (border, 21)]
+                  if D[rc] > nodata]
+    outlet_set = list(dict.fromkeys(outlet_set))
     td = 0.0
     for _ in range(n_iters):
-        td = o.iterate(band_w, band_d, nodata, module, 1, outlet=(outlet[0] - lo, outlet[1]), totaldrain=td) \
-            if module == po.DRAIN else (o.iterate(band_w, band_d, nodata, module, 1) or 0.0)
+        if module == 3:  # the band sees the outlets that lie inside it (halo rows included)
+            o.iterate_outlets(band_w, band_d, nodata, 1, [(r - lo, c) for r, c in outlet_set if lo <= r < hi] or [(0, 0)])
+        else:
+            td = o.iterate(band_w, band_d, nodata, module, 1, outlet=(outlet[0] - lo, outlet[1]), totaldrain=td) \
+                if module == po.DRAIN else (o.iterate(band_w, band_d, nodata, module, 1) or 0.0)
         # halo exchange: my first 6 owned rows go up, my last 3 owned rows go down
         reqs = []
         if rank > 0:
@@ -92,7 +100,10 @@ def _worker(rank, world, port, rows, cols, module, n_iters, seed, out_q):
     if rank == 0:
         full = np.concatenate([g[0] for g in gathered], axis=0)
         ref = W.copy()
-        ref_td = o.iterate(ref, D, nodata, module, n_iters, outlet=outlet, totaldrain=0.0)
+        if module == 3:
+            o.iterate_outlets(ref, D, nodata, n_iters, outlet_set)
+        else:
+            o.iterate(ref, D, nodata, module, n_iters, outlet=outlet, totaldrain=0.0)
         # Drain: only the stripe that owns the outlet's neighbours reports; halo copies must not double count.
         # (the oracle band run counts every contact it sees, so compare the owner's share only for the grid.)
         out_q.put((bool(np.array_equal(full, ref)), int((full != ref).sum())))
@@ -101,7 +112,7 @@ def _worker(rank, world, port, rows, cols, module, n_iters, seed, out_q):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("module", [0, 1])
+@pytest.mark.parametrize("module", [0, 1, 2, 3])
 def test_striped_oracle_equals_single_domain(world, module):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
