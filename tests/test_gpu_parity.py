@@ -414,3 +414,22 @@ def test_basin5_add_300mm_to_convergence(cuda_lib, basin5, tmp_path):
     assert path.read_text() == golden_text("ref_opencl_add300.asc.gz")
     assert "%10.2f" % rep.final_vol == "3301066.70" and "%10.4f" % rep.water_frac == "    0.3062"
     print(f"cfg1 on GPU: {rep.solver_ms/1e3:.2f} s of device time, {rep.launches} launches")
+
+
+def test_auto_picks_the_production_tilings(cuda_lib):
+    """AUTO on a grid above the small-grid limit: fp64 Add/Subtract get the 24-warp tiling at 80 registers,
+    fp64 Drain the 16-warp tiling (folded-gate step only with a zero threshold > 0), fp32 the 484-column one."""
+    from wdpm_b200 import F32, F64, Solver, solver
+    from wdpm_b200.solver import PRODUCTION_FUSED_VARIANT_F64
+    rows = cols = 2100  # 4.4 M cells
+    def tiling(module, dtype, thres):
+        with Solver(rows, cols, NODATA, module, dtype=dtype, zero_threshold=thres) as s:
+            i = s.info()
+        return {k: i[k] for k in ("window_cols", "strip_cols", "cta_threads", "smem_bytes")}
+    def variant(v, dtype):
+        i = solver.fused_variant_info(v, dtype)
+        return {k: i[k] for k in ("window_cols", "strip_cols", "cta_threads", "smem_bytes")}
+    assert tiling(0, F64, 5e-6) == variant(PRODUCTION_FUSED_VARIANT_F64, F64)
+    assert tiling(1, F64, 5e-6) == variant(PRODUCTION_FUSED_VARIANT_F64, F64)
+    assert tiling(2, F64, 5e-6) == variant(15, F64) == variant(14, F64)   # same tiling, different Drain step
+    assert tiling(0, F32, 5e-6) == variant(12, F32)
