@@ -26,12 +26,16 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     rows, cols = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (700, 900)
     failures = []
-    for dt, code in ((np.float64, F64), (np.float32, F32)):
-        for module in (0, 1, 2):
+    # chunk_rows 0 = the solver's own chunking (one wave of CTAs at this size); 3 = one row triple per CTA, i.e.
+    # several waves: a stripe's upward halo is then exported, and its flag raised, long before its kernel ends
+    cases = [(dt, code, module, 0) for dt, code in ((np.float64, F64), (np.float32, F32)) for module in (0, 1, 2)]
+    cases += [(np.float64, F64, 0, 3), (np.float64, F64, 2, 3)]
+    for dt, code, module, chunk_rows in cases:
+        if True:
             rng = np.random.default_rng(99)
             D, W = random_case(rng, rows, cols, dt, depth=0.05)
             dem, w0 = D[1:-1, 1:-1], W[1:-1, 1:-1]
-            ds = DistributedSolver(rows, cols, -99999.0, module, device=local, dtype=code, zero_threshold=1e-3)
+            ds = DistributedSolver(rows, cols, -99999.0, module, device=local, dtype=code, zero_threshold=1e-3, fused_chunk_rows=chunk_rows)
             st = ds.stripe
             ds.upload_band(dem[st.band_row0:st.band_row0 + st.band_rows], w0[st.band_row0:st.band_row0 + st.band_rows])
             if module == 0:
@@ -71,7 +75,7 @@ def main():
                     if module == 2:
                         ok = ok and dt(a.total_drain) == dt(b.total_drain)
                 if not ok:
-                    failures.append((dt.__name__, module))
+                    failures.append((dt.__name__, module, chunk_rows))
                 s.close()
             ds.close()
     if rank == 0:
