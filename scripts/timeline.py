@@ -2,7 +2,7 @@
 """Per-warp timeline of one CTA of the fused kernel (developer probe).
 
 Build (here, no GPU needed):   python scripts/timeline.py --build
-Run (GPU box):                 python scripts/timeline.py --size 8192 --variant 11 --out gpurun_out/tl_v11.npy
+Run (GPU box):                 python scripts/timeline.py --size 8192 [--dtype f32] [--module 2] [--variant V] --cta 70 --out gpurun_out/tl.npy
 
 The instrumented library is the product source compiled with -DWDPM_TIMELINE into
 wdpm_b200/libwdpm_b200_tl.so; each warp's lane 0 stamps clock64 at fixed points of eight steps:
@@ -23,6 +23,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--build", action="store_true")
 ap.add_argument("--size", type=int, default=8192)
 ap.add_argument("--variant", type=int, default=0)
+ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+ap.add_argument("--module", type=int, default=0, help="0 add, 1 subtract, 2 drain (uniform 300 mm water layer)")
 ap.add_argument("--cta", type=int, default=300)
 ap.add_argument("--step0", type=int, default=100)
 ap.add_argument("--out", default="gpurun_out/timeline.npy")
@@ -40,14 +42,23 @@ os.environ["WDPM_B200_LIB"] = str(TL_LIB)
 sys.path.insert(0, str(ROOT))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
-from wdpm_b200 import ADD, F64, Solver, synth  # noqa: E402
+from wdpm_b200 import ADD, F32, F64, Solver, synth  # noqa: E402
 from wdpm_b200.solver import load_library  # noqa: E402
 
 lib = load_library()
-dem = synth.fractal_dem(a.size, a.size, seed=a.size, device="cuda", dtype=torch.float64).cpu().numpy()
-s = Solver(a.size, a.size, -99999.0, ADD, dtype=F64, zero_threshold=5e-6, kernel=2, fused_variant=a.variant)
-s.upload(dem, None)
-s.apply_add(0.3, 1.0)
+dem = synth.fractal_dem(a.size, a.size, seed=a.size, device="cuda", dtype=torch.float64)
+if a.dtype == "f32":
+    dem = dem - dem.min()
+dem = dem.to(torch.float64 if a.dtype == "f64" else torch.float32).cpu().numpy()
+s = Solver(a.size, a.size, -99999.0, a.module, dtype=F64 if a.dtype == "f64" else F32, zero_threshold=5e-6, kernel=2, fused_variant=a.variant)
+if a.module == ADD:
+    s.upload(dem, None)
+    s.apply_add(0.3, 1.0)
+else:
+    s.upload(dem, np.full_like(dem, 0.3))
+    if a.module == 2:
+        s.find_outlet()
+        s.set_total_drain(0.0)
 s.run_block(20)
 assert lib.wdpm_debug_timeline(a.cta, a.step0, None, 0) == 0
 r = s.run_block(10)
@@ -61,7 +72,9 @@ print("ms/iteration", r.iterate_ms / 10, s.info())
 t0 = tl[:, :, 0][tl[:, :, 0] > 0].min()
 for step in range(1, 4):
     print("step", step)
-    for w in range(25):
+    for w in range(32):
+        if not tl[step, w, 0]:
+            continue
         row = tl[step, w]
         print(f"  warp {w:2d}: " + " ".join(f"{(x - t0) if x > 0 else -1:7d}" for x in row[:9]))
 s.close()
