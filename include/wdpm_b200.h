@@ -58,6 +58,7 @@ extern "C" {
 #define WDPM_E_NOMEM -3  /* host or device allocation failed */
 #define WDPM_E_STATE -4  /* call out of order (e.g. run before upload) */
 #define WDPM_E_UNSUPPORTED -5
+#define WDPM_E_HALO -6   /* stripes: a neighbour's halo did not arrive (WDPM_B200_HALO_TIMEOUT_MS, default 120 s); upload again */
 
 typedef struct wdpm_solver wdpm_solver; /* opaque; owns all device memory */
 
@@ -154,6 +155,12 @@ int wdpm_quantize_water(wdpm_solver *s);
 /* water depth at one cell (for totaldrain = max(bigwater[outlet],0), src/WDPMCL.c:1029) */
 int wdpm_get_cell_water(wdpm_solver *s, int32_t row, int32_t col, double *value);
 
+/* Order-free 64-bit checksum of the water grid this solver owns (interior cells): sum of
+ * bits(w) * (2*index + 1) mod 2^64, index = row-major position in the WHOLE DEM. The sum of the stripes' checksums
+ * (mod 2^64) equals the single-solver checksum iff the grids are equal bit for bit, whatever the partition.
+ * New work (benchmark / consistency evidence); the reference has no counterpart. */
+int wdpm_water_checksum(wdpm_solver *s, uint64_t *checksum);
+
 /* One convergence block, all on the device, no host round trip inside:
  * zero-threshold + snapshot (src/WDPMCL.c:1055-1073), n_iters iterations of the
  * nine colour sub-passes (:1184-1206 with src/runoff.cl), then the masked
@@ -192,7 +199,8 @@ typedef struct wdpm_info {
     int32_t smem_bytes;
     int32_t iters_per_launch;
     int32_t sm_count;
-    int32_t reserved[7];
+    int32_t warp_autonomous; /* fused: 1 = the warp-autonomous kernel (two tiles per lane, warp shuffles), 0 = k_fused */
+    int32_t reserved[6];
 } wdpm_info;
 int wdpm_get_info(wdpm_solver *s, wdpm_info *info);
 /* Tiling of fused variant `variant` (1-based) for `dtype`; returns WDPM_E_ARG past the last one. */

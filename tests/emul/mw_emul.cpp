@@ -192,6 +192,182 @@ int run_launches(T* w_padded, const T* d_padded, int R, int C, T nodata, int n_l
     return 0;
 }
 
+// Warp-autonomous variant (k_fused_wa): the same row march; the tiles of a row triple are relaxed by KW warps
+// of 32 lanes, each lane holding a 3 x 8 window that slides by warp shuffle. Modelled exactly: all warps of a
+// row group read their windows before any of them writes back (the kernel's row-group mbarrier), lane 31
+// stores nothing, shuffles take the right-hand lane's value (lane 31 keeps its own).
+template <typename T, int MODULE, typename CFG, bool FAST, bool GUARD>
+void run_cta_wa(const Layout& L, const T* w_in, T* w_out, const T* dem, int strip, int chunk,
+                int chunk_triples, int total_triples, Errors& err, std::vector<unsigned char>& stored_mask) {
+    constexpr int W = CFG::W, NT = CFG::NT, NPH = CFG::NPH, NRING = CFG::NRING, PF = CFG::PF, KW = CFG::KW;
+    MwTile<CFG> tile;
+    tile.init(strip, chunk, chunk_triples, total_triples);
+    std::vector<T> ring_w((size_t)NRING * W), ring_d((size_t)NRING * W);
+    std::vector<int> slot_row(NRING, INT32_MIN);
+    std::deque<std::vector<int>> groups;
+    std::vector<int> slot_pending(NRING, 0);
+    const int col0 = tile.x0 + kPadLeft;
+
+    auto issue_loads = [&](int s) {
+        for (int t = 0; t < NT; t++) {
+            const int m = tile.triple(s, 0, t);
+            if (!tile.staged(m)) continue;
+            for (int k = 0; k < 3; k++) {
+                const int row = 3 * m + k;
+                const int slot = tile.ring_slot(row);
+                if (slot_pending[slot]) err.load_over_store++;
+                const size_t src = (size_t)(row + kPadTop) * L.pitch + col0;
+                std::memcpy(&ring_w[(size_t)slot * W], w_in + src, W * sizeof(T));
+                std::memcpy(&ring_d[(size_t)slot * W], dem + src, W * sizeof(T));
+                slot_row[slot] = row;
+            }
+        }
+    };
+    auto wait_read = [&](size_t allowed) {
+        while (groups.size() > allowed) {
+            for (int slot : groups.front()) slot_pending[slot]--;
+            groups.pop_front();
+        }
+    };
+    struct Lane { T wt[3][8], dd[3][8]; };
+    std::vector<Lane> lanes((size_t)KW * 32);
+
+    for (int s = 0; s < PF && s < tile.n_steps; s++) issue_loads(s);
+    for (int s = 0; s < tile.n_steps; s++) {
+        if (s + PF < tile.n_steps) issue_loads(s + PF);
+        for (int grp = 0; grp < NPH * NT; grp++) {
+            const int t = grp % NT, ph = grp / NT;
+            const int m = tile.triple(s, ph, t);
+            if (!tile.runnable(m, ph)) continue;
+            const int row0 = 3 * m + ph;
+            int sl[3];
+            sl[0] = tile.ring_slot(row0);
+            sl[1] = sl[0] + 1 == NRING ? 0 : sl[0] + 1;
+            sl[2] = sl[1] + 1 == NRING ? 0 : sl[1] + 1;
+            for (int r = 0; r < 3; r++)
+                if (slot_row[sl[r]] != row0 + r) err.wrong_row++;
+            for (int kw = 0; kw < KW; kw++)
+                for (int lane = 0; lane < 32; lane++) {
+                    Lane& ln = lanes[(size_t)kw * 32 + lane];
+                    const int cb = CFG::WSTRIDE * kw + CFG::CPL * lane;
+                    if (cb + 8 > W) { err.wrong_row++; continue; }
+                    for (int r = 0; r < 3; r++) {
+                        for (int c = 0; c < 6; c++) ln.wt[r][c] = ring_w[(size_t)sl[r] * W + cb + c];
+                        for (int c = 0; c < 8; c++) ln.dd[r][c] = ring_d[(size_t)sl[r] * W + cb + c];
+                        ln.wt[r][6] = ln.wt[r][7] = T(0);
+                    }
+                }
+            for (int kw = 0; kw < KW; kw++) {
+                Lane* wl = &lanes[(size_t)kw * 32];
+                for (int lane = 0; lane < 32; lane++) wa_relax_pair<T, MODULE, 0, FAST, GUARD>(wl[lane].wt, wl[lane].dd);
+                for (int lane = 0; lane < 32; lane++)
+                    for (int r = 0; r < 3; r++) wl[lane].wt[r][6] = wl[lane < 31 ? lane + 1 : lane].wt[r][0];
+                for (int lane = 0; lane < 32; lane++) wa_relax_pair<T, MODULE, 1, FAST, GUARD>(wl[lane].wt, wl[lane].dd);
+                for (int lane = 0; lane < 32; lane++)
+                    for (int r = 0; r < 3; r++) wl[lane].wt[r][7] = wl[lane < 31 ? lane + 1 : lane].wt[r][1];
+                for (int lane = 0; lane < 32; lane++) wa_relax_pair<T, MODULE, 2, FAST, GUARD>(wl[lane].wt, wl[lane].dd);
+            }
+            for (int kw = 0; kw < KW; kw++)
+                for (int lane = 0; lane < 31; lane++) {
+                    const Lane& ln = lanes[(size_t)kw * 32 + lane];
+                    const int cb = CFG::WSTRIDE * kw + CFG::CPL * lane;
+                    for (int r = 0; r < 3; r++)
+                        for (int c = 2; c < 8; c++) ring_w[(size_t)sl[r] * W + cb + c] = ln.wt[r][c];
+                }
+        }
+        std::vector<int> grp;
+        for (int t = 0; t < NT; t++) {
+            const int m = tile.triple(s, NPH - 1, t);
+            for (int k = 0; k < 3; k++) {
+                const int row = 3 * m + 2 + k;
+                if (!tile.owns_row(row)) continue;
+                const int slot = tile.ring_slot(row);
+                if (slot_row[slot] != row) err.wrong_row++;
+                const size_t dst = (size_t)(row + kPadTop) * L.pitch + col0 + CFG::HL;
+                std::memcpy(w_out + dst, &ring_w[(size_t)slot * W + CFG::HL], CFG::TWV * sizeof(T));
+                for (int c = 0; c < CFG::TWV; c++) {
+                    if (stored_mask[dst + c]) err.double_store++;
+                    stored_mask[dst + c] = 1;
+                }
+                grp.push_back(slot);
+                slot_pending[slot]++;
+            }
+        }
+        if (!grp.empty()) groups.push_back(grp);
+        wait_read(1);
+    }
+    wait_read(0);
+}
+
+template <typename T, int MODULE, typename CFG, bool FAST, bool GUARD>
+int run_launches_wa(T* w_padded, const T* d_padded, int R, int C, T nodata, int n_launches, int chunk_triples, long long* err_out) {
+    Layout L;
+    L.R = R; L.C = C;
+    const int n_strips = (C + 2 + CFG::TWV - 1) / CFG::TWV;
+    const int total_triples = (R + 2 + 2) / 3;
+    L.pitch = ((kPadLeft + n_strips * CFG::TWV + (CFG::W - CFG::TWV - CFG::HL) + 31) / 32) * 32;
+    L.nrows_dev = kPadTop + 3 * (total_triples + 2 * kMaxItersPerLaunch) + 3;
+    if (chunk_triples <= 0) chunk_triples = total_triples;
+    const int n_chunks = (total_triples + chunk_triples - 1) / chunk_triples;
+    const size_t n = (size_t)L.pitch * L.nrows_dev;
+    std::vector<T> dem(n, invalid_elevation<T>()), wa(n, T(0)), wb(n, T(0));
+    for (int i = 0; i < R + 2; i++)
+        for (int j = 0; j < C + 2; j++) {
+            dem[L.at(i, j)] = mask_elevation(d_padded[(size_t)i * (C + 2) + j], nodata);
+            wa[L.at(i, j)] = w_padded[(size_t)i * (C + 2) + j];
+        }
+    Errors err;
+    T* cur = wa.data();
+    T* nxt = wb.data();
+    for (int l = 0; l < n_launches; l++) {
+        std::vector<unsigned char> stored(n, 0);
+        for (int chunk = 0; chunk < n_chunks; chunk++)
+            for (int strip = 0; strip < n_strips; strip++)
+                run_cta_wa<T, MODULE, CFG, FAST, GUARD>(L, cur, nxt, dem.data(), strip, chunk, chunk_triples, total_triples, err, stored);
+        for (int i = 0; i < R + 2; i++)
+            for (int j = 0; j < C + 2; j++)
+                if (!stored[L.at(i, j)]) err.unstored++;
+        T* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    long long margin_dirty = 0;
+    {
+        std::vector<unsigned char> inside(n, 0);
+        for (int i = 0; i < R + 2; i++)
+            for (int j = 0; j < C + 2; j++) inside[L.at(i, j)] = 1;
+        for (size_t k = 0; k < n; k++)
+            if (!inside[k] && cur[k] != T(0)) margin_dirty++;
+    }
+    for (int i = 0; i < R + 2; i++)
+        for (int j = 0; j < C + 2; j++) w_padded[(size_t)i * (C + 2) + j] = cur[L.at(i, j)];
+    err_out[0] = err.wrong_row;
+    err_out[1] = err.load_over_store;
+    err_out[2] = err.double_store;
+    err_out[3] = err.unstored;
+    err_out[4] = margin_dirty;
+    return 0;
+}
+
+// mode: bit 0 = fast Add step, bit 1 = no activity guard (fp64 Add on a clean grid only)
+template <typename T, typename CFG>
+int dispatch_wa(int module, int mode, T* w, const T* d, int R, int C, T nodata, int n, int ct, long long* e) {
+    if (module == kAdd && mode == 3) return run_launches_wa<T, kAdd, CFG, true, false>(w, d, R, C, nodata, n, ct, e);
+    if (module == kAdd && mode == 1) return run_launches_wa<T, kAdd, CFG, true, true>(w, d, R, C, nodata, n, ct, e);
+    if (module == kAdd) return run_launches_wa<T, kAdd, CFG, false, true>(w, d, R, C, nodata, n, ct, e);
+    if (module == kSubtract) return run_launches_wa<T, kSubtract, CFG, false, true>(w, d, R, C, nodata, n, ct, e);
+    return -1;
+}
+
+template <typename T>
+int dispatch_wa_cfg(int cfg, int module, int mode, T* w, const T* d, int R, int C, T nodata, int n, int ct, long long* e) {
+    switch (cfg) {
+        case 0: return dispatch_wa<T, WaCfg<1, 1, 1>>(module, mode, w, d, R, C, nodata, n, ct, e);
+        case 1: return dispatch_wa<T, WaCfg<2, 2, 1>>(module, mode, w, d, R, C, nodata, n, ct, e);
+        case 2: return dispatch_wa<T, WaCfg<2, 1, 2>>(module, mode, w, d, R, C, nodata, n, ct, e);
+        case 3: return dispatch_wa<T, WaCfg<3, 1, 1>>(module, mode, w, d, R, C, nodata, n, ct, e);
+    }
+    return -2;
+}
+
 template <typename T, typename CFG>
 int dispatch_module(int module, T* w, const T* d, int R, int C, T nodata, int n, int ct, int dr, int dc, T* td, long long* e) {
     switch (module) {
@@ -238,6 +414,23 @@ int mw_emul_cfg_info(int cfg, int* W, int* TWV, int* K, int* NRING) {
 int mw_emul_run_f64(int cfg, int module, double* w, const double* d, int R, int C, double nodata, int n_launches,
                     int chunk_triples, int drainrow, int draincol, double* totaldrain, long long* errors5) {
     return dispatch_cfg<double>(cfg, module, w, d, R, C, nodata, n_launches, chunk_triples, drainrow, draincol, totaldrain, errors5);
+}
+int wa_emul_cfg_info(int cfg, int* W, int* TWV) {
+    switch (cfg) {
+        case 0: *W = WaCfg<1, 1, 1>::W; *TWV = WaCfg<1, 1, 1>::TWV; return 0;
+        case 1: *W = WaCfg<2, 2, 1>::W; *TWV = WaCfg<2, 2, 1>::TWV; return 0;
+        case 2: *W = WaCfg<2, 1, 2>::W; *TWV = WaCfg<2, 1, 2>::TWV; return 0;
+        case 3: *W = WaCfg<3, 1, 1>::W; *TWV = WaCfg<3, 1, 1>::TWV; return 0;
+    }
+    return -1;
+}
+int wa_emul_run_f64(int cfg, int module, int mode, double* w, const double* d, int R, int C, double nodata, int n_launches,
+                    int chunk_triples, long long* errors5) {
+    return dispatch_wa_cfg<double>(cfg, module, mode, w, d, R, C, nodata, n_launches, chunk_triples, errors5);
+}
+int wa_emul_run_f32(int cfg, int module, int mode, float* w, const float* d, int R, int C, float nodata, int n_launches,
+                    int chunk_triples, long long* errors5) {
+    return dispatch_wa_cfg<float>(cfg, module, mode, w, d, R, C, nodata, n_launches, chunk_triples, errors5);
 }
 int mw_emul_run_f32(int cfg, int module, float* w, const float* d, int R, int C, float nodata, int n_launches,
                     int chunk_triples, int drainrow, int draincol, float* totaldrain, long long* errors5) {

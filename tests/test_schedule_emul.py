@@ -100,3 +100,59 @@ def test_hazard_checks_fire_when_ring_is_too_small():
     D, W = random_case(rng, 50, 70, np.float64)
     _, err = run_emul(lib, 7, po.ADD, W.copy(), D, -99999.0, 1, 0)
     assert err[0] > 0 or err[1] > 0
+
+
+# ---- warp-autonomous schedule (k_fused_wa): two tiles per lane, windows sliding by warp shuffle ----
+
+def run_wa(lib, cfg, module, mode, w, d, nodata, n_launches, chunk_triples):
+    sfx, ct = ("_f64", C.c_double) if w.dtype == np.float64 else ("_f32", C.c_float)
+    R, Cc = w.shape[0] - 2, w.shape[1] - 2
+    err = np.zeros(5, dtype=np.int64)
+    rc = getattr(lib, "wa_emul_run" + sfx)(cfg, module, mode, w.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), R, Cc,
+                                          ct(nodata), n_launches, chunk_triples, err.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return err
+
+
+@pytest.mark.parametrize("cfg", range(4))
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_wa_schedule_is_bit_exact(oracle, emul, cfg, dt):
+    """Grids narrower and wider than one strip (several warps per row triple, several strips), chunked rows."""
+    rng = np.random.default_rng(300 + cfg)
+    W_, TWV = C.c_int(), C.c_int()
+    emul.wa_emul_cfg_info(cfg, C.byref(W_), C.byref(TWV))
+    for rows, cols, chunk_triples in ((40, 70, 0), (31, TWV.value + 40, 4), (25, 2 * TWV.value + 7, 3), (1, 1, 0), (3, 200, 1)):
+        for mod, mode in ((po.ADD, 0), (po.ADD, 1), (po.SUBTRACT, 0)):
+            D, Wt = random_case(rng, rows, cols, dt)
+            a, b = Wt.copy(), Wt.copy()
+            oracle.iterate(a, D, -99999.0, mod, 3)
+            err = run_wa(emul, cfg, mod, mode, b, D, -99999.0, 3, chunk_triples)
+            assert not err.any(), (cfg, rows, cols, mod, err)
+            assert np.array_equal(a, b), (cfg, rows, cols, mod, mode, int((a != b).sum()))
+
+
+def test_wa_unguarded_add_on_a_clean_grid(oracle, emul):
+    """No activity test at all (fp64 Add, kOptNoGuard): exact as long as the water is +0 wherever the reference
+    skips the centre - dry cells, NODATA cells and the halo ring included - which is what the solver checks."""
+    rng = np.random.default_rng(41)
+    for cfg, rows, cols, ct in ((0, 40, 300, 5), (1, 33, 420, 0)):
+        D, Wt = random_case(rng, rows, cols, np.float64, wet_fraction=0.5, nodata_fraction=0.15)
+        assert not np.signbit(Wt).any() and not Wt[D <= -99999.0].any()
+        a, b = Wt.copy(), Wt.copy()
+        oracle.iterate(a, D, -99999.0, po.ADD, 4)
+        err = run_wa(emul, cfg, po.ADD, 3, b, D, -99999.0, 4, ct)
+        assert not err.any() and np.array_equal(a, b)
+        assert not np.signbit(b).any()  # the invariant is preserved
+
+
+def test_wa_guard_handles_what_the_unguarded_step_must_not_see(oracle, emul):
+    """Negative water, -0.0 and water on NODATA cells: the guarded step treats them as the reference does."""
+    rng = np.random.default_rng(43)
+    D, Wt = random_case(rng, 30, 260, np.float64, wet_fraction=0.8, nodata_fraction=0.1)
+    Wt[rng.uniform(size=Wt.shape) < 0.05] = -0.25
+    Wt[rng.uniform(size=Wt.shape) < 0.05] = -0.0
+    Wt[D <= -99999.0] = 0.125
+    a, b = Wt.copy(), Wt.copy()
+    oracle.iterate(a, D, -99999.0, po.ADD, 3)
+    err = run_wa(emul, 0, po.ADD, 0, b, D, -99999.0, 3, 4)
+    assert not err.any() and np.array_equal(a, b) and np.array_equal(np.signbit(a), np.signbit(b))

@@ -53,6 +53,22 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+HOOKS_LIB = ROOT / "tests" / "_build" / "libwdpm_b200_hooks.so"
+
+
+def build_hooks_library(force: bool = False) -> Path:
+    """TEST build of the same sources with -DWDPM_TEST_HOOKS (tests/test_gpu_halo_race.py): lets a test delay
+    chosen CTAs and switch the halo protocol back to its pre-fix CTA count, to show that the race it guards
+    against is real. Lives under tests/_build; the product never loads it."""
+    if force or _stale(HOOKS_LIB, SOURCES + HEADERS):
+        HOOKS_LIB.parent.mkdir(parents=True, exist_ok=True)
+        cmd = [_nvcc(), *NVCC_FLAGS, "-DWDPM_TEST_HOOKS", "-ccbin", "/usr/bin/g++", "-o", str(HOOKS_LIB), *map(str, SOURCES)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc (test hooks) failed:\n" + res.stdout + res.stderr)
+    return HOOKS_LIB
+
+
 def build_host(force: bool = False) -> Path | None:
     """The drop-in command-line host (C) linked against the library."""
     src = PKG / "host" / "wdpm_host.c"

@@ -88,16 +88,33 @@ __global__ void k_quantize_water(T* __restrict__ w, const T* __restrict__ d, lon
         if (is_valid_elevation(d[a])) w[a] = (T)wdpm_quantize6((double)w[a]);
 }
 
-// Block prologue (src/WDPMCL.c:1055-1073): w < thres -> 0 over the whole padded
-// grid (margins are 0 and stay 0), then snapshot.
+// Does any cell that is not a valid DEM cell (NODATA, halo ring, margins) hold water != +0? (Never after the first
+// block prologue for the reference's own files; the solver only needs to KNOW, see wdpm_solver::water_clean.)
 template <typename T>
-__global__ void k_block_prologue(T* __restrict__ w, T* __restrict__ oldw, long long n, T thres) {
+__global__ void k_check_invalid_water(const T* __restrict__ w, const T* __restrict__ d, long long n, int* __restrict__ dirty) {
+    bool bad = false;
+    for (long long a = blockIdx.x * (long long)blockDim.x + threadIdx.x; a < n; a += (long long)gridDim.x * blockDim.x) {
+        const T v = w[a];
+        bad = bad || (!is_valid_elevation(d[a]) && !(v == T(0) && !signbit(v)));
+    }
+    if (bad) *dirty = 1;
+}
+
+// Block prologue (src/WDPMCL.c:1055-1073): w < thres -> 0 over the whole padded
+// grid (margins are 0 and stay 0), then snapshot. Also reports whether any invalid cell still holds
+// water afterwards (k_check_invalid_water's question, asked again because the threshold pass is what
+// clears the NODATA values a water file carries).
+template <typename T>
+__global__ void k_block_prologue(T* __restrict__ w, T* __restrict__ oldw, const T* __restrict__ d, long long n, T thres, int* __restrict__ dirty) {
+    bool bad = false;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         T v = w[i];
         if (v < thres) v = T(0);
         w[i] = v;
         oldw[i] = v;
+        bad = bad || (!is_valid_elevation(d[i]) && !(v == T(0) && !signbit(v)));
     }
+    if (bad) *dirty = 1;
 }
 
 // ---------------------------------------------------------------------------
@@ -169,6 +186,29 @@ __global__ void k_block_reduce_stage2(const BlockPartial* __restrict__ partials,
         }
         *out = p;
     }
+}
+
+// Order-free 64-bit checksum of the interior water cells this solver owns: sum over cells of
+// bits(w) * (2 * index + 1) modulo 2^64, index = the cell's position in the WHOLE DEM (row-major,
+// 0-based). Integer addition commutes, so stripes can be summed in any order and the result does not depend
+// on how the DEM is partitioned: equal checksums at 1, 2, 4, 8 GPUs mean equal grids (bit patterns and
+// positions). Benchmarks report it; nothing in the solver reads it.
+template <typename T>
+__global__ void k_water_checksum(const T* __restrict__ w, Geom g, int first_row, int n_rows, int global_row0, int dem_cols,
+                                 unsigned long long* __restrict__ out) {
+    unsigned long long acc = 0;
+    for (int i = first_row + blockIdx.x; i < first_row + n_rows; i += gridDim.x) {
+        const size_t base = dev_index(g, i, 0);
+        const unsigned long long row_index = (unsigned long long)(global_row0 + i - 1) * (unsigned long long)dem_cols;
+        for (int j = 1 + threadIdx.x; j <= g.C; j += blockDim.x) {
+            unsigned long long bits;
+            if (sizeof(T) == 8) bits = (unsigned long long)__double_as_longlong((double)w[base + j]);
+            else bits = (unsigned long long)(unsigned)__float_as_int((float)w[base + j]);
+            acc += bits * (2ull * (row_index + (unsigned long long)(j - 1)) + 1ull);
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
 // ---------------------------------------------------------------------------
@@ -349,15 +389,27 @@ __device__ __forceinline__ void st_release_sys(int* p, int v) {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Hold the stream until both neighbours' halos of iteration `epoch` have landed.
-__global__ void k_halo_wait(HaloFlags* flags, int need_above, int need_below, int epoch) {
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Hold the stream until both neighbours' halos of iteration `epoch` have landed. A neighbour that does not
+// show up within `timeout_ns` (dead rank, host stuck for longer than the host allows) sets the sticky
+// HaloFlags::error; every later wait then returns at once, and the host reports WDPM_E_HALO at the end of
+// the block (solver.cu, block_end_t) instead of a water grid computed on stale halo rows.
+__global__ void k_halo_wait(HaloFlags* flags, int need_above, int need_below, int epoch, unsigned long long timeout_ns) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    for (long long spins = 0;; spins++) {
+    if (ld_acquire_sys(&flags->error)) return;
+    const unsigned long long t0 = global_timer_ns();
+    for (unsigned spins = 0;; spins++) {
         const bool ok_a = !need_above || ld_acquire_sys(&flags->from_above) >= epoch;
         const bool ok_b = !need_below || ld_acquire_sys(&flags->from_below) >= epoch;
         if (ok_a && ok_b) return;
-        if (spins > 40000000ll) {  // ~10 s: a neighbour died; flag the error instead of hanging the GPU
+        if ((spins & 63u) == 63u && global_timer_ns() - t0 > timeout_ns) {
             flags->error = 1;
+            __threadfence_system();
             return;
         }
         __nanosleep(200);
@@ -454,8 +506,13 @@ struct FusedParams {
     HaloFlags* self_flags;
     HaloFlags* up_flags;
     HaloFlags* dn_flags;
-    int up_ctas, dn_ctas;  // CTAs that own rows exported upwards / downwards (the last of them raises the flag)
+    int up_ctas, dn_ctas;  // CTAs counted in before the upward / downward flag rises (the last of them raises it)
     int epoch;
+#ifdef WDPM_TEST_HOOKS
+    // Test builds only (tests/test_gpu_halo_race.py; never compiled into the product library):
+    int dbg_old_dn_count;    // count only the CTAs that OWN exported rows, as the kernel did before the fix
+    int dbg_reader_delay_ns; // CTAs that only READ the bottom halo sleep this long before their first load
+#endif
 };
 
 template <typename CFG, typename T>
@@ -479,6 +536,10 @@ constexpr int kOptRegRealloc = 2;
 constexpr int kOptDrainFast = 4;
 __host__ __device__ constexpr int fused_extra_threads(int opt) { return (opt & kOptRegRealloc) ? 128 : 32; }
 
+#ifdef WDPM_TEST_HOOKS
+__device__ int g_dbg_counters[4];  // 0: reader CTAs delayed
+#endif
+
 #ifdef WDPM_TIMELINE
 // Developer probe (never compiled into the product library): per-warp clock64 stamps of one CTA.
 constexpr int kTlSteps = 8, kTlWarps = 32, kTlPoints = 10;
@@ -493,6 +554,130 @@ __device__ int g_timeline_cta = 300, g_timeline_step0 = 100;
 #else
 #define WDPM_TL(point) do { } while (0)
 #endif
+
+// ---------------------------------------------------------------------------
+// Data movement of the iteration kernels (k_fused, k_fused_wa): one elected lane of a dedicated warp
+// issues every bulk copy. Per step: write home the rows the last phase finished in the step before
+// (plus, for row stripes, the copies into the neighbours' halo rows), release ring slots once their
+// write-back has read them, prefetch the rows of step s + PF. At the end: the halo handshake.
+// ---------------------------------------------------------------------------
+
+template <typename CFG>
+__device__ __forceinline__ bool step_has_loads(const MwTile<CFG>& tile, int s) {
+    for (int t = 0; t < CFG::NT; t++)
+        if (tile.staged(tile.triple(s, 0, t))) return true;
+    return false;
+}
+
+template <typename CFG, typename T>
+__device__ __forceinline__ void issue_row_loads(const FusedParams<T>& p, const MwTile<CFG>& tile, T* ring_w, T* ring_d, uint64_t* bars, int s) {
+    constexpr uint32_t kRowBytes = CFG::W * sizeof(T);
+    const size_t col0 = (size_t)(tile.x0 + kPadLeft);  // device column of window column 0; multiple of 4 elements by construction
+    uint64_t* bar = &bars[s % CFG::NSTAGE];
+    int nrows = 0;
+    for (int t = 0; t < CFG::NT; t++)
+        if (tile.staged(tile.triple(s, 0, t))) nrows += 3;
+    if (nrows == 0) return;
+    mbar_expect_tx(bar, (uint32_t)(2 * nrows) * kRowBytes);
+    for (int t = 0; t < CFG::NT; t++) {
+        const int m = tile.triple(s, 0, t);
+        if (!tile.staged(m)) continue;
+        for (int k = 0; k < 3; k++) {
+            const int row = 3 * m + k;
+            const size_t src = (size_t)(row + kPadTop) * (size_t)p.g.pitch + col0;
+            const int slot = tile.ring_slot(row);
+            bulk_load(ring_w + (size_t)slot * CFG::W, p.w_in + src, kRowBytes, bar);
+            bulk_load(ring_d + (size_t)slot * CFG::W, p.dem + src, kRowBytes, bar);
+        }
+    }
+}
+
+// rows finished by the last phase in step s: C-type rows 3m+2 .. 3m+4
+template <typename CFG, typename T>
+__device__ __forceinline__ void issue_row_stores(const FusedParams<T>& p, const MwTile<CFG>& tile, T* ring_w, int s) {
+    const size_t col0 = (size_t)(tile.x0 + kPadLeft);
+    bool any = false;
+    for (int t = 0; t < CFG::NT; t++) {
+        const int m = tile.triple(s, CFG::NPH - 1, t);
+        for (int k = 0; k < 3; k++) {
+            const int row = 3 * m + 2 + k;
+            if (!tile.owns_row(row)) continue;
+            const size_t dst = (size_t)(row + kPadTop) * (size_t)p.g.pitch + col0 + CFG::HL;
+            const T* src = ring_w + (size_t)tile.ring_slot(row) * CFG::W + CFG::HL;
+            bulk_store(p.w_out + dst, src, CFG::TWV * sizeof(T));
+            if (p.up_out && row < kHaloBelow)  // ... and into the bottom halo of the stripe above
+                bulk_store(p.up_out + (size_t)(row + p.P_up + kPadTop) * (size_t)p.g.pitch + col0 + CFG::HL, src, CFG::TWV * sizeof(T));
+            if (p.dn_out && row >= p.P_self - kHaloAbove && row < p.P_self)  // ... the top halo of the stripe below
+                bulk_store(p.dn_out + (size_t)(row - p.P_self + kPadTop) * (size_t)p.g.pitch + col0 + CFG::HL, src, CFG::TWV * sizeof(T));
+            any = true;
+        }
+    }
+    if (any) bulk_commit();
+}
+
+// NBAR = CTA-wide barriers per step the compute threads execute (this warp takes part in each)
+template <typename CFG, typename T, int NBAR>
+__device__ __forceinline__ void data_movement_warp(const FusedParams<T>& p, const MwTile<CFG>& tile, T* ring_w, T* ring_d, uint64_t* bars, bool lead) {
+    constexpr int PF = CFG::PF;
+#ifdef WDPM_TEST_HOOKS
+    if (lead && p.dn_flags && p.dbg_reader_delay_ns > 0 && 3 * tile.m1 > p.P_self - kHaloBelow &&
+        3 * tile.m1 <= p.P_self - kHaloAbove) {  // reads rows [P, P+3) of w_in but exports nothing: make it late
+        const unsigned long long t0 = global_timer_ns();
+        while (global_timer_ns() - t0 < (unsigned long long)p.dbg_reader_delay_ns) __nanosleep(1000);
+        atomicAdd(&g_dbg_counters[0], 1);
+        // has the stripe below already finished the NEXT iteration (whose export overwrites the halo rows I am about to read)?
+        if (ld_acquire_sys(&p.self_flags->from_below) > p.epoch) atomicAdd(&g_dbg_counters[1], 1);
+    }
+#endif
+    if (lead)
+        for (int s = 0; s < PF && s < tile.n_steps; s++) issue_row_loads<CFG, T>(p, tile, ring_w, ring_d, bars, s);
+    for (int s = 0; s < tile.n_steps; s++) {
+        WDPM_TL(0);
+        if (lead) {
+            if (s > 0) {
+                issue_row_stores<CFG, T>(p, tile, ring_w, s - 1);
+                // ring slots reused by the next prefetch must have been read out by their stores:
+                // only the group committed just now may still be in flight
+                bulk_wait_read<1>();
+            }
+            if (s + PF < tile.n_steps) issue_row_loads<CFG, T>(p, tile, ring_w, ring_d, bars, s + PF);
+        }
+        __syncwarp();
+        WDPM_TL(1);
+#pragma unroll
+        for (int b = 0; b < NBAR; b++) __syncthreads();
+        WDPM_TL(8);
+    }
+    if (lead) {
+        issue_row_stores<CFG, T>(p, tile, ring_w, tile.n_steps - 1);
+        bulk_wait_read<0>();
+        const bool exp_up = p.up_flags && 3 * tile.m0 < kHaloBelow;
+        // downwards the flag also licenses the stripe below to overwrite MY bottom-halo rows [P, P+kHaloBelow) in the
+        // buffer this iteration reads, so every CTA that STAGES one of those rows counts (3*(m1+BOT_TRIPLES) > P), not
+        // only those that own the exported rows; such a CTA may export nothing and only bumps the counter.
+#ifdef WDPM_TEST_HOOKS
+        const int dn_reach = p.dbg_old_dn_count ? kHaloAbove : kHaloBelow;
+#else
+        constexpr int dn_reach = kHaloBelow;
+#endif
+        const bool exp_dn = p.dn_flags && 3 * tile.m1 > p.P_self - dn_reach && 3 * tile.m0 < p.P_self;
+        if (exp_up || exp_dn) {
+            // my rows have landed, also in the neighbour's memory; the CTA that is last to say so raises the flag
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            __threadfence_system();
+            if (exp_up && atomicAdd(&p.self_flags->push_count, 1) == p.up_ctas - 1) {
+                p.self_flags->push_count = 0;
+                __threadfence_system();
+                st_release_sys(&p.up_flags->from_below, p.epoch);
+            }
+            if (exp_dn && atomicAdd(&p.self_flags->push_count_dn, 1) == p.dn_ctas - 1) {
+                p.self_flags->push_count_dn = 0;
+                __threadfence_system();
+                st_release_sys(&p.dn_flags->from_above, p.epoch);
+            }
+        }
+    }
+}
 
 template <typename T, int MODULE, typename CFG, int NTHREADS, int MINB, int OPT = 0>
 __global__ void __launch_bounds__(NTHREADS + fused_extra_threads(OPT), MINB)
@@ -537,55 +722,6 @@ k_fused(const FusedParams<T> p) {
     }
     const bool cta_has_outlets = MODULE == kDrain && s_cta_has_outlets != 0;
 
-    constexpr uint32_t kRowBytes = W * sizeof(T);
-    // device column of window column 0; multiple of 4 elements by construction
-    const size_t col0 = (size_t)(tile.x0 + kPadLeft);
-
-    auto issue_loads = [&](int s) {  // thread 0 only: stage the A-type rows of step s
-        uint64_t* bar = &bars[s % NSTAGE];
-        int nrows = 0;
-        for (int t = 0; t < NT; t++)
-            if (tile.staged(tile.triple(s, 0, t))) nrows += 3;
-        if (nrows == 0) return;
-        mbar_expect_tx(bar, (uint32_t)(2 * nrows) * kRowBytes);
-        for (int t = 0; t < NT; t++) {
-            const int m = tile.triple(s, 0, t);
-            if (!tile.staged(m)) continue;
-            for (int k = 0; k < 3; k++) {
-                const int row = 3 * m + k;
-                const size_t src = (size_t)(row + kPadTop) * (size_t)p.g.pitch + col0;
-                const int slot = tile.ring_slot(row);
-                bulk_load(ring_w + (size_t)slot * W, p.w_in + src, kRowBytes, bar);
-                bulk_load(ring_d + (size_t)slot * W, p.dem + src, kRowBytes, bar);
-            }
-        }
-    };
-    auto step_has_loads = [&](int s) {
-        for (int t = 0; t < NT; t++)
-            if (tile.staged(tile.triple(s, 0, t))) return true;
-        return false;
-    };
-
-    auto issue_stores = [&](int s) {  // rows finished by the last phase in step s: C-type rows 3m+2 .. 3m+4
-        bool any = false;
-        for (int t = 0; t < NT; t++) {
-            const int m = tile.triple(s, NPH - 1, t);
-            for (int k = 0; k < 3; k++) {
-                const int row = 3 * m + 2 + k;
-                if (!tile.owns_row(row)) continue;
-                const size_t dst = (size_t)(row + kPadTop) * (size_t)p.g.pitch + col0 + CFG::HL;
-                const T* src = ring_w + (size_t)tile.ring_slot(row) * W + CFG::HL;
-                bulk_store(p.w_out + dst, src, CFG::TWV * sizeof(T));
-                if (p.up_out && row < kHaloBelow)  // ... and into the bottom halo of the stripe above
-                    bulk_store(p.up_out + (size_t)(row + p.P_up + kPadTop) * (size_t)p.g.pitch + col0 + CFG::HL, src, CFG::TWV * sizeof(T));
-                if (p.dn_out && row >= p.P_self - kHaloAbove && row < p.P_self)  // ... the top halo of the stripe below
-                    bulk_store(p.dn_out + (size_t)(row - p.P_self + kPadTop) * (size_t)p.g.pitch + col0 + CFG::HL, src, CFG::TWV * sizeof(T));
-                any = true;
-            }
-        }
-        if (any) bulk_commit();
-    };
-
     // Barriers. The colour sub-steps of a step only order tiles of the SAME row triple (they exchange
     // window columns); different row groups touch disjoint rows within a step. When every row group
     // is a whole number of warps and each thread owns one tile (GROUPED), the two inner barriers are
@@ -601,50 +737,7 @@ k_fused(const FusedParams<T> p) {
             asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
             if (tid >= NTHREADS + 32) return;  // the rest of the fourth warp group only lent its registers
         }
-        const bool lead = tid == NTHREADS;
-        if (lead)
-            for (int s = 0; s < PF && s < tile.n_steps; s++) issue_loads(s);
-        for (int s = 0; s < tile.n_steps; s++) {
-            WDPM_TL(0);
-            if (lead) {
-                if (s > 0) {
-                    issue_stores(s - 1);
-                    // ring slots reused by the next prefetch must have been read out by their stores:
-                    // only the group committed just now may still be in flight
-                    bulk_wait_read<1>();
-                }
-                if (s + PF < tile.n_steps) issue_loads(s + PF);
-            }
-            __syncwarp();
-            WDPM_TL(1);
-            if (!GROUPED) {
-                __syncthreads();
-                __syncthreads();
-            }
-            __syncthreads();
-            WDPM_TL(8);
-        }
-        if (lead) {
-            issue_stores(tile.n_steps - 1);
-            bulk_wait_read<0>();
-            const bool exp_up = p.up_flags && 3 * tile.m0 < kHaloBelow;
-            const bool exp_dn = p.dn_flags && 3 * tile.m1 > p.P_self - kHaloAbove && 3 * tile.m0 < p.P_self;
-            if (exp_up || exp_dn) {
-                // my rows have landed, also in the neighbour's memory; the CTA that is last to say so raises the flag
-                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-                __threadfence_system();
-                if (exp_up && atomicAdd(&p.self_flags->push_count, 1) == p.up_ctas - 1) {
-                    p.self_flags->push_count = 0;
-                    __threadfence_system();
-                    st_release_sys(&p.up_flags->from_below, p.epoch);
-                }
-                if (exp_dn && atomicAdd(&p.self_flags->push_count_dn, 1) == p.dn_ctas - 1) {
-                    p.self_flags->push_count_dn = 0;
-                    __threadfence_system();
-                    st_release_sys(&p.dn_flags->from_above, p.epoch);
-                }
-            }
-        }
+        data_movement_warp<CFG, T, GROUPED ? 1 : 3>(p, tile, ring_w, ring_d, bars, tid == NTHREADS);
         return;
     }
 
@@ -713,7 +806,7 @@ k_fused(const FusedParams<T> p) {
     };
     for (int s = 0; s < tile.n_steps; s++) {
         WDPM_TL(0);
-        if (step_has_loads(s)) mbar_wait(&bars[s % NSTAGE], (uint32_t)((s / NSTAGE) & 1));
+        if (step_has_loads<CFG>(tile, s)) mbar_wait(&bars[s % NSTAGE], (uint32_t)((s / NSTAGE) & 1));
         WDPM_TL(1);
         prepare(s);
 #pragma unroll
@@ -786,6 +879,149 @@ k_fused(const FusedParams<T> p) {
         __syncthreads();
         WDPM_TL(8);
 
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Warp-autonomous iteration kernel (mw_schedule.h, WaCfg). Same row march, ring, bulk copies and halo
+// export as k_fused; the tiles of a row triple are relaxed by KW self-contained warps:
+//   * a lane holds two adjacent tiles in a 3 x 8 register window (16-byte shared-memory loads: the window
+//     starts at a multiple of 6 columns), relaxes both in every colour sub-pass (two independent chains,
+//     interleaved) and slides the window by taking the entering column from the lane to its right with
+//     warp shuffles - no shared-memory round trip and no barrier between the sub-passes;
+//   * per step a warp reads its window once (water 3 x 6, elevations 3 x 8) and writes back 3 x 6;
+//   * the warps of a row triple read columns their neighbours write back (the 6-column overlap), so a
+//     warp announces "my window is in registers" on the row group's mbarrier and waits for the others'
+//     announcements only just before its write-back - by then long satisfied;
+//   * one CTA barrier per step, with the data-movement warp.
+// OPT: kOptAddFast / kOptRegRealloc as in k_fused; kOptNoGuard (fp64 Add): no activity test at all
+// (relax.cuh, wa_relax_pair) - the solver selects it only while the water grid is known to be +0 wherever
+// the reference would skip the centre.
+// ---------------------------------------------------------------------------
+
+constexpr int kOptNoGuard = 8;
+
+template <typename CFG, typename T>
+constexpr size_t wa_smem_bytes() {
+    return (size_t)2 * CFG::NRING * CFG::W * sizeof(T) + (CFG::NSTAGE + CFG::NPH * CFG::NT) * sizeof(uint64_t) + 16;
+}
+
+template <typename T> struct Vec2;
+template <> struct Vec2<double> { using type = double2; };
+template <> struct Vec2<float> { using type = float2; };
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ T shfl_from_right(T v) {
+    return __shfl_down_sync(0xffffffffu, v, 1);
+}
+
+template <typename T, int MODULE, typename CFG, int OPT>
+__global__ void __launch_bounds__(CFG::NWARPS * 32 + fused_extra_threads(OPT), 1)
+k_fused_wa(const FusedParams<T> p) {
+    constexpr int NTHREADS = CFG::NWARPS * 32;
+    constexpr int NALL = NTHREADS + fused_extra_threads(OPT);
+    constexpr bool REALLOC = (OPT & kOptRegRealloc) != 0;
+    constexpr int kLaunchRegs = (65536 / NALL) & ~7;
+    constexpr int kComputeRegsRaw = ((kLaunchRegs * NALL - 128 * 24) / NTHREADS) & ~7;
+    constexpr int kComputeRegs = kComputeRegsRaw > 232 ? 232 : kComputeRegsRaw;
+    static_assert(!REALLOC || (NTHREADS % 128 == 0 && kComputeRegs > kLaunchRegs), "register reallocation needs whole warp groups");
+    constexpr int W = CFG::W, NT = CFG::NT, NPH = CFG::NPH, NRING = CFG::NRING, NSTAGE = CFG::NSTAGE, KW = CFG::KW;
+    constexpr bool FAST = sizeof(T) == 8 && (OPT & kOptAddFast) && MODULE == kAdd;
+    constexpr bool GUARD = !(FAST && (OPT & kOptNoGuard));
+    using V2 = typename Vec2<T>::type;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* ring_w = reinterpret_cast<T*>(smem_raw);
+    T* ring_d = ring_w + (size_t)NRING * W;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring_d + (size_t)NRING * W);
+    uint64_t* group_bars = bars + NSTAGE;  // one per row group: "every warp of the group holds its window in registers"
+
+    const int tid = threadIdx.x;
+    const int strip = blockIdx.x % p.n_strips;
+    const int chunk = blockIdx.x / p.n_strips;
+    MwTile<CFG> tile;
+    tile.init(strip, chunk, p.chunk_triples, p.total_triples);
+
+    if (tid == 0) {
+        for (int i = 0; i < NSTAGE; i++) mbar_init(&bars[i], 1);
+        for (int i = 0; i < NPH * NT; i++) mbar_init(&group_bars[i], KW);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (tid >= NTHREADS) {
+        if (REALLOC) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+            if (tid >= NTHREADS + 32) return;
+        }
+        data_movement_warp<CFG, T, 1>(p, tile, ring_w, ring_d, bars, tid == NTHREADS);
+        return;
+    }
+    if (REALLOC) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kComputeRegs));
+
+    // this warp: phase ph (= colour row offset, K = 1), triple slot t, column block kw of the row triple
+    const int warp = tid >> 5, lane = tid & 31;
+    const int kw = warp % KW, grp = warp / KW, t = grp % NT, ph = grp / NT;
+    const int cb = CFG::WSTRIDE * kw + CFG::CPL * lane;  // window column of the lane's column 0
+    const bool stores = lane < 31;
+    constexpr int DOFF = NRING * W;
+    uint64_t* gbar = &group_bars[grp];
+
+    for (int s = 0; s < tile.n_steps; s++) {
+        const int m = tile.m_lo + NT * s - ph * CFG::LAG + t;
+        const bool run = tile.runnable(m, ph);
+        if (ph == 0 && step_has_loads<CFG>(tile, s)) mbar_wait(&bars[s % NSTAGE], (uint32_t)((s / NSTAGE) & 1));
+        if (run) {
+            const int row0 = 3 * m + ph;
+            int s0 = tile.ring_slot(row0);
+            int s1 = s0 + 1; if (s1 == NRING) s1 = 0;
+            int s2 = s1 + 1; if (s2 == NRING) s2 = 0;
+            T* wrow[3] = {ring_w + s0 * W + cb, ring_w + s1 * W + cb, ring_w + s2 * W + cb};
+            T wt[3][8], dd[3][8];
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+#pragma unroll
+                for (int v = 0; v < 3; v++) {
+                    const V2 x = *reinterpret_cast<const V2*>(wrow[r] + 2 * v);
+                    wt[r][2 * v] = x.x; wt[r][2 * v + 1] = x.y;
+                }
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    const V2 x = *reinterpret_cast<const V2*>(wrow[r] + DOFF + 2 * v);
+                    dd[r][2 * v] = x.x; dd[r][2 * v + 1] = x.y;
+                }
+            }
+            wa_relax_pair<T, MODULE, 0, FAST, GUARD>(wt, dd);
+            // every lane's window is in registers (the relax above consumed it): tell the row group
+            __syncwarp();
+            if (lane == 0) mbar_arrive(gbar);
+#pragma unroll
+            for (int r = 0; r < 3; r++) wt[r][6] = shfl_from_right(wt[r][0]);
+            wa_relax_pair<T, MODULE, 1, FAST, GUARD>(wt, dd);
+#pragma unroll
+            for (int r = 0; r < 3; r++) wt[r][7] = shfl_from_right(wt[r][1]);
+            wa_relax_pair<T, MODULE, 2, FAST, GUARD>(wt, dd);
+            // the neighbouring warps of this row triple read columns I am about to overwrite: they must hold them by now
+            if (KW > 1) mbar_wait(gbar, (uint32_t)(s & 1));
+            if (stores) {
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+#pragma unroll
+                    for (int v = 1; v < 4; v++) {
+                        V2 x; x.x = wt[r][2 * v]; x.y = wt[r][2 * v + 1];
+                        *reinterpret_cast<V2*>(wrow[r] + 2 * v) = x;
+                    }
+                }
+            }
+        } else {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(gbar);  // keep the group barrier's phase in step with s
+        }
+        fence_proxy_async();  // make this step's smem writes visible to the bulk-store engine
+        __syncthreads();
     }
 }
 

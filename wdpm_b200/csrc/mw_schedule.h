@@ -73,6 +73,39 @@ struct MwCfg {
     static_assert(HL <= kPadLeft, "left halo exceeds the device margin");
 };
 
+// Tiling of the WARP-AUTONOMOUS iteration kernel (kernels.cuh, k_fused_wa). Rows march exactly as above (same
+// phases, lags, ring, loads and write-backs); what differs is who relaxes the tiles of a row triple.
+// Every lane owns TWO column-adjacent tiles (6 columns) and keeps them, water and elevations, in a
+// 3 x 8 register window for the three colour sub-passes of a step; the window slides one column per sub-pass:
+// the entering column comes from the lane to the right by warp shuffle (that lane's leaving column). A
+// warp is therefore self-contained: no shared-memory traffic and no barrier between sub-passes. The price is
+// that a warp's last lane cannot slide (nobody to its right inside the warp): it recomputes the first
+// columns of the next warp only to feed lane 30, and stores nothing. A warp spans 32*6 = 192 columns of which
+// lanes 0..30 finish and store the columns [2, 188) relative to the warp's start; consecutive warps start
+// WSTRIDE = 186 columns apart so that these ranges abut. The window's own edges lose 2 columns (left) and
+// 4 (right) per phase exactly as the halo analysis above says (8 and 16 over the three phases of an iteration).
+template <int KW_, int NT_, int PF_>
+struct WaCfg {
+    static constexpr int KW = KW_;        // warps per row triple
+    static constexpr int NT = NT_;        // row triples per phase per step
+    static constexpr int K = 1;           // iterations per launch
+    static constexpr int PF = PF_;        // prefetch distance in steps
+    static constexpr int NPH = 3;
+    static constexpr int LAG = NT + 1;
+    static constexpr int CPL = 6;                    // columns (two tiles) per lane
+    static constexpr int WSTRIDE = 31 * CPL;         // columns finished per warp = distance between warp starts
+    static constexpr int W = ((KW * WSTRIDE + CPL + 2 + 3) / 4) * 4;  // last warp's lane 31 reads columns up to KW*WSTRIDE + 7
+    static constexpr int HL = 12;                    // needs >= 8; multiple of 12 keeps 16 B alignment and the colour phase
+    static constexpr int TWV = ((KW * WSTRIDE - 10 - HL) / 12) * 12;  // valid after three phases: [8, KW*WSTRIDE - 10)
+    static constexpr int TOP_TRIPLES = 1;
+    static constexpr int BOT_TRIPLES = 2;
+    static constexpr int NRING_MIN = 3 * NT * (PF + 2) + 3 * (NPH - 1) * LAG - 2;
+    static constexpr int NRING = ((NRING_MIN + 2) / 3) * 3 + WDPM_NRING_DELTA;
+    static constexpr int NSTAGE = PF + 1;
+    static constexpr int NWARPS = NPH * NT * KW;     // compute warps
+    static_assert(TWV > 0 && HL <= kPadLeft && W % 4 == 0, "window geometry");
+};
+
 // Per-CTA view of the schedule. All rows/cols are PADDED grid coordinates
 // (row 0 / col 0 = the reference's halo ring); they may be negative or exceed the
 // grid inside the device margins, which hold dem = nodata, water = 0.

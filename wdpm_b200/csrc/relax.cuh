@@ -253,6 +253,58 @@ WDPM_HD void relax_window5(T (&w)[3][5], const T (&d)[3][5]) {
     w[1][COFS + 1] = wc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-autonomous kernel (kernels.cuh, k_fused_wa): a lane owns TWO column-adjacent tiles and keeps a
+// 3 x 8 register window (water and elevations) that slides one column per colour sub-pass; in sub-pass
+// C the tiles are columns C..C+2 and C+3..C+5. The two tiles of a sub-pass are disjoint, so their
+// eight-step chains are independent and are written interleaved (instruction-level parallelism: the
+// FP64 latency of one chain hides behind the other).
+//
+// No branch around an inactive centre (it would serialise the two chains): a centre the reference
+// would not relax (dry, or not a valid cell: runoff.cl:145) runs the same eight steps on the
+// substitutes dc := -S/2, wc := +0. Then sc = -S/2, h = sc - sn < 0 for every neighbour (surfaces are
+// > -S/2 and finite), every gate is closed, every amount moved is -0.0 (or nothing, for the predicated
+// forms): an exact no-op on all nine cells; the centre's own value is put back afterwards.
+template <typename T>
+WDPM_HD T inactive_elevation() { return T(-0.5) * invalid_elevation<T>(); }
+
+template <typename T, int MODULE, bool FAST>
+WDPM_HD void push_sel(T dc, T& wc, T dn, T& wn) {
+    if (FAST && MODULE == kAdd && sizeof(T) == 8) push_add_fast<T>(dc, wc, dn, wn);
+    else if (FAST && MODULE == kDrain && sizeof(T) == 8) push_drain_fast<T>(dc, wc, dn, wn);
+    else push<T, MODULE>(dc, wc, dn, wn);
+}
+
+// GUARD = false: the caller guarantees that every centre may run unguarded, i.e. water is +0 wherever the
+// reference would skip the centre (no water on invalid cells, no negative water, no -0.0) - then a skipped
+// centre moves +0 everywhere, which changes nothing. fp64 Add only (solver.cu decides).
+template <typename T, int MODULE, int C, bool FAST, bool GUARD>
+WDPM_HD void wa_relax_pair(T (&w)[3][8], const T (&d)[3][8]) {
+    T dcA = d[1][C + 1], dcB = d[1][C + 4];
+    T wcA = w[1][C + 1], wcB = w[1][C + 4];
+    const T keepA = wcA, keepB = wcB;
+    bool actA = true, actB = true;
+    if (GUARD) {
+        actA = (wcA > T(0)) && is_valid_elevation(dcA);
+        actB = (wcB > T(0)) && is_valid_elevation(dcB);
+        dcA = actA ? dcA : inactive_elevation<T>();
+        dcB = actB ? dcB : inactive_elevation<T>();
+        wcA = actA ? wcA : T(0);
+        wcB = actB ? wcB : T(0);
+    }
+#define WDPM_PUSH2(r, c)                                                  \
+    do {                                                                  \
+        push_sel<T, MODULE, FAST>(dcA, wcA, d[r][C + c], w[r][C + c]);          \
+        push_sel<T, MODULE, FAST>(dcB, wcB, d[r][C + 3 + c], w[r][C + 3 + c]);  \
+    } while (0)
+    WDPM_PUSH2(0, 0); WDPM_PUSH2(0, 1); WDPM_PUSH2(0, 2);
+    WDPM_PUSH2(1, 0); WDPM_PUSH2(1, 2);
+    WDPM_PUSH2(2, 0); WDPM_PUSH2(2, 1); WDPM_PUSH2(2, 2);
+#undef WDPM_PUSH2
+    w[1][C + 1] = (!GUARD || actA) ? wcA : keepA;
+    w[1][C + 4] = (!GUARD || actB) ? wcB : keepB;
+}
+
 // The eight neighbour steps of one tile (only meaningful when t.active). FAST selects the fp64 Add
 // rewrite (push_add_fast; in fp32 the predicated form of move_if measured faster); the plain form is what the colour kernel - the
 // second, independent CUDA path - and the CPU checks run.

@@ -17,8 +17,9 @@ using namespace wdpm;
 
 namespace {
 
-constexpr int kDefaultVariantF64 = 13;  // 384-column window, two row triples per phase, 24 compute warps at 80 registers, Add fast step
-constexpr int kDefaultVariantF32 = 12;  // 484-column window (160 tiles = 5 whole warps per row group, named barriers), two CTAs of 15 compute warps per SM
+constexpr int kDefaultVariantF64 = 17;  // warp-autonomous: 380-column window, two row triples per phase, 12 compute warps x 2 tiles per lane at 160 registers, Add fast step
+constexpr int kDefaultVariantF32 = 16;  // warp-autonomous: 752-column window, 24 compute warps x 2 tiles per lane
+constexpr int kDefaultVariantF32Drain = 12;  // k_fused: 484-column window (160 tiles = 5 whole warps per row group, named barriers), two CTAs of 15 compute warps per SM
 constexpr int kDefaultVariantF64DrainFast = 15;  // ... with the folded-gate Drain step (zero threshold > 0)
 constexpr int kDefaultVariantF64Drain = 14;  // Drain needs ~110 registers: 16 compute warps at 112 (register reallocation), 512 columns
 // Grids of a few hundred thousand cells (the reference's basin5 is 482 x 471) cannot fill 148 SMs
@@ -54,8 +55,10 @@ using FusedLaunchFn = cudaError_t (*)(const FusedParams<T>&, int grid, cudaStrea
 template <typename T>
 struct FusedVariant {
     int W, TWV, HL, K, NT, PF, nthreads, minb;
+    bool wa = false;  // k_fused_wa
     size_t smem;
-    FusedLaunchFn<T> launch[3];
+    FusedLaunchFn<T> launch[3];        // per module; nullptr = this variant does not implement the module
+    FusedLaunchFn<T> launch_clean[3];  // used instead while wdpm_solver::water_clean holds (nullptr = none)
     cudaError_t (*prepare)();
 };
 
@@ -86,7 +89,41 @@ FusedVariant<T> make_variant() {
     v.launch[kAdd] = launch_fused<T, kAdd, CFG, NTHREADS, MINB, OPT>;
     v.launch[kSubtract] = launch_fused<T, kSubtract, CFG, NTHREADS, MINB, OPT>;
     v.launch[kDrain] = launch_fused<T, kDrain, CFG, NTHREADS, MINB, OPT>;
+    v.launch_clean[kAdd] = v.launch_clean[kSubtract] = v.launch_clean[kDrain] = nullptr;
     v.prepare = prepare_fused<T, CFG, NTHREADS, MINB, OPT>;
+    return v;
+}
+
+// Warp-autonomous variants (kernels.cuh, k_fused_wa): Add and Subtract only.
+template <typename T, int MODULE, typename CFG, int OPT>
+cudaError_t launch_wa(const FusedParams<T>& p, int grid, cudaStream_t st) {
+    k_fused_wa<T, MODULE, CFG, OPT><<<grid, CFG::NWARPS * 32 + fused_extra_threads(OPT), wa_smem_bytes<CFG, T>(), st>>>(p);
+    return cudaGetLastError();
+}
+
+template <typename T, typename CFG, int OPT>
+cudaError_t prepare_wa() {
+    const int smem = (int)wa_smem_bytes<CFG, T>();
+    cudaError_t e;
+    e = cudaFuncSetAttribute(k_fused_wa<T, kAdd, CFG, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_fused_wa<T, kAdd, CFG, OPT | kOptNoGuard>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_fused_wa<T, kSubtract, CFG, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
+template <typename T, typename CFG, int OPT = 0>
+FusedVariant<T> make_wa_variant() {
+    FusedVariant<T> v;
+    v.W = CFG::W; v.TWV = CFG::TWV; v.HL = CFG::HL; v.K = CFG::K; v.NT = CFG::NT; v.PF = CFG::PF;
+    v.nthreads = CFG::NWARPS * 32; v.minb = 1; v.wa = true;
+    v.smem = wa_smem_bytes<CFG, T>();
+    v.launch[kAdd] = launch_wa<T, kAdd, CFG, OPT>;
+    v.launch[kSubtract] = launch_wa<T, kSubtract, CFG, OPT>;
+    v.launch[kDrain] = nullptr;
+    v.launch_clean[kAdd] = (sizeof(T) == 8 && (OPT & kOptAddFast)) ? launch_wa<T, kAdd, CFG, OPT | kOptNoGuard> : nullptr;
+    v.launch_clean[kSubtract] = v.launch_clean[kDrain] = nullptr;
+    v.prepare = prepare_wa<T, CFG, OPT>;
     return v;
 }
 
@@ -115,6 +152,11 @@ const std::vector<FusedVariant<double>>& fused_variants<double>() {
         make_variant<double, MwCfg<512, 1, 1, 2>, 512, 1, kOptRegRealloc>(),                // 14: as 1, compute warps at 112 registers
         make_variant<double, MwCfg<512, 1, 1, 2>, 512, 1, kOptRegRealloc | kOptDrainFast>(), // 15: as 14, Drain with the gate folded into the factor
         make_variant<double, MwCfg<64, 1, 1, 1>, 128, 1, kOptDrainFast>(),                  // 16: test window for 15
+        make_wa_variant<double, WaCfg<2, 2, 1>, kOptAddFast | kOptRegRealloc>(),            // 17: warp-autonomous, 12 warps x 2 tiles per lane, 380-column window
+        make_wa_variant<double, WaCfg<1, 1, 1>, kOptAddFast>(),                             // 18: test window (196 columns, 3 warps) for 17
+        make_wa_variant<double, WaCfg<2, 2, 1>, kOptAddFast>(),                             // 19: as 17 without register reallocation
+        make_wa_variant<double, WaCfg<2, 1, 1>, kOptAddFast>(),                             // 20: one triple per phase (6 warps; small grids)
+        make_wa_variant<double, WaCfg<3, 1, 1>, kOptAddFast>(),                             // 21: 566-column window, one triple per phase (9 warps)
     };
     return v;
 }
@@ -134,6 +176,9 @@ const std::vector<FusedVariant<float>>& fused_variants<float>() {
         make_variant<float, MwCfg<580, 1, 1, 2>, 576, 2>(),    // 11: 192 tiles per row group (whole warps), two CTAs per SM
         make_variant<float, MwCfg<484, 1, 1, 2>, 480, 2>(),    // 12: 160 tiles per row group, two CTAs per SM
         make_variant<float, MwCfg<772, 2, 1, 1>, 768, 1>(),    // 13: 256 tiles per row group... one CTA per SM
+        make_wa_variant<float, WaCfg<2, 2, 1>, kOptRegRealloc>(),  // 14: warp-autonomous, 12 warps x 2 tiles per lane
+        make_wa_variant<float, WaCfg<1, 1, 1>>(),                  // 15: test window for 14
+        make_wa_variant<float, WaCfg<4, 2, 1>, kOptRegRealloc>(),  // 16: 752-column window, 24 warps
     };
     return v;
 }
@@ -162,6 +207,12 @@ struct wdpm_solver {
     void* oldw = nullptr;
     int cur = 0;
     bool have_dem = false;
+    // water_clean: the current water grid is +0 (not negative, not -0.0, not water on an invalid cell) wherever
+    // the reference would skip the centre, so the unguarded Add step may run (relax.cuh, wa_relax_pair).
+    // True after a block prologue with a zero threshold > 0 (WDPMCL.c:1055-1065 wipes negatives and -0.0)
+    // provided the last upload put no water on invalid cells (invalid_dry); the kernels preserve both.
+    bool water_clean = false, invalid_dry = false;
+    int* d_dirty = nullptr;   // device flag of k_check_invalid_water
 
     // Drain outlets (kernels.cuh "Drain bookkeeping"): capacity kMaxOutlets
     void* totaldrain = nullptr;    // T[kMaxOutlets] per-outlet accumulators
@@ -193,6 +244,9 @@ struct wdpm_solver {
         bool ipc = false;
     } above, below;
     int epoch = 0;             // halo pushes done since the last upload
+    unsigned long long halo_timeout_ns = 120ull * 1000000000ull;  // WDPM_B200_HALO_TIMEOUT_MS; k_halo_wait gives up after this
+    bool halo_failed = false;  // a wait gave up: results since then are void until the next upload
+    int* h_halo_error = nullptr;  // pinned copy of HaloFlags::error
 
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -271,17 +325,28 @@ void set_halo_export(wdpm_solver* s, FusedParams<T>& p) {
     p.up_flags = up ? s->above.flags : nullptr;
     p.dn_flags = dn ? s->below.flags : nullptr;
     p.up_ctas = p.dn_ctas = 0;
+    int dn_reach = kHaloBelow;  // every CTA that reads my bottom-halo rows counts, see k_fused
+#ifdef WDPM_TEST_HOOKS
+    p.dbg_old_dn_count = getenv("WDPM_TEST_HALO_OLD_COUNT") ? atoi(getenv("WDPM_TEST_HALO_OLD_COUNT")) : 0;
+    p.dbg_reader_delay_ns = getenv("WDPM_TEST_HALO_READER_DELAY_NS") ? atoi(getenv("WDPM_TEST_HALO_READER_DELAY_NS")) : 0;
+    if (p.dbg_old_dn_count) dn_reach = kHaloAbove;
+#endif
     for (int c = 0; c < s->n_chunks; c++) {  // the kernel's own test, per chunk of rows (all strips of a chunk agree)
         const int m0 = c * s->chunk_triples;
         const int m1 = m0 + s->chunk_triples < s->total_triples ? m0 + s->chunk_triples : s->total_triples;
         if (up && 3 * m0 < kHaloBelow) p.up_ctas += s->n_strips;
-        if (dn && 3 * m1 > s->P - kHaloAbove && 3 * m0 < s->P) p.dn_ctas += s->n_strips;
+        if (dn && 3 * m1 > s->P - dn_reach && 3 * m0 < s->P) p.dn_ctas += s->n_strips;
     }
     p.epoch = s->epoch;
 }
 
 template <typename T>
 int fused_launch_only(wdpm_solver* s);
+
+template <typename T>
+FusedLaunchFn<T> pick_launch(const wdpm_solver* s, const FusedVariant<T>& v) {
+    return (s->water_clean && v.launch_clean[s->module]) ? v.launch_clean[s->module] : v.launch[s->module];
+}
 
 template <typename T>
 int fused_iterations(wdpm_solver* s, int n) {
@@ -299,11 +364,11 @@ int fused_iterations(wdpm_solver* s, int n) {
         p.launch_parity = s->launch_parity;
         p.ds = drain_state<T>(s);
         if (s->stripe && s->epoch > 0 && (s->above.present || s->below.present)) {
-            k_halo_wait<<<1, 32, 0, s->stream>>>(s->flags, s->above.present, s->below.present, s->epoch);
+            k_halo_wait<<<1, 32, 0, s->stream>>>(s->flags, s->above.present, s->below.present, s->epoch, s->halo_timeout_ns);
             s->launches++;
         }
         set_halo_export<T>(s, p);  // the launch also pushes the halo rows and raises the neighbours' flags
-        CUDA_TRY(v.launch[s->module](p, s->n_strips * s->n_chunks, s->stream));
+        CUDA_TRY(pick_launch<T>(s, v)(p, s->n_strips * s->n_chunks, s->stream));
         s->launches++;
         s->cur ^= 1;
         s->launch_parity ^= 1;
@@ -333,7 +398,7 @@ int fused_launch_only(wdpm_solver* s) {
     p.launch_parity = s->launch_parity;
     p.ds = drain_state<T>(s);
     set_halo_export<T>(s, p);
-    CUDA_TRY(v.launch[s->module](p, s->n_strips * s->n_chunks, s->stream));
+    CUDA_TRY(pick_launch<T>(s, v)(p, s->n_strips * s->n_chunks, s->stream));
     s->launches++;
     s->cur ^= 1;
     s->launch_parity ^= 1;
@@ -403,11 +468,13 @@ int block_begin_t(wdpm_solver* s) {
     CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
     if (s->stripe && s->epoch > 0 && (s->above.present || s->below.present)) {
         // the neighbours' last halo push must land before the threshold pass touches the halo rows
-        k_halo_wait<<<1, 32, 0, s->stream>>>(s->flags, s->above.present, s->below.present, s->epoch);
+        k_halo_wait<<<1, 32, 0, s->stream>>>(s->flags, s->above.present, s->below.present, s->epoch, s->halo_timeout_ns);
         s->launches++;
     }
+    if (s->cfg.zero_threshold > 0.0 && s->invalid_dry) s->water_clean = true;  // no negative water, no -0.0 left (see wdpm_solver)
+    CUDA_TRY(cudaMemsetAsync(s->d_dirty, 0, sizeof(int), s->stream));
     k_block_prologue<T><<<grid_for(n, 256, s->sm_count), 256, 0, s->stream>>>(
-        static_cast<T*>(s->w[s->cur]), static_cast<T*>(s->oldw), n, (T)s->cfg.zero_threshold);
+        static_cast<T*>(s->w[s->cur]), static_cast<T*>(s->oldw), static_cast<const T*>(s->dem), n, (T)s->cfg.zero_threshold, s->d_dirty);
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(s->ev[1], s->stream));
@@ -426,8 +493,17 @@ int block_end_t(wdpm_solver* s, wdpm_block_result* out) {
     CUDA_TRY(cudaMemcpyAsync(s->h_result, s->d_result, sizeof(BlockPartial), cudaMemcpyDeviceToHost, s->stream));
     std::vector<T> tds((size_t)(s->n_outlets > 0 ? s->n_outlets : 1), T(0));
     CUDA_TRY(cudaMemcpyAsync(tds.data(), s->totaldrain, sizeof(T) * tds.size(), cudaMemcpyDeviceToHost, s->stream));
+    if (s->stripe) CUDA_TRY(cudaMemcpyAsync(s->h_halo_error, &s->flags->error, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    int dirty = 1;
+    CUDA_TRY(cudaMemcpyAsync(&dirty, s->d_dirty, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (s->stripe && *s->h_halo_error) {
+        s->in_block = false;
+        s->halo_failed = true;
+        return fail(WDPM_E_HALO, "a neighbouring stripe's halo did not arrive in time (WDPM_B200_HALO_TIMEOUT_MS): the block's results are void; upload again");
+    }
+    s->invalid_dry = dirty == 0;  // as of this block's prologue; the kernels never put water on an invalid cell
     T td = tds[0];  // one outlet: the reference's totaldrain; a set: summed in outlet order, solver precision
     for (size_t k = 1; k < tds.size(); k++) td = td + tds[k];
     s->in_block = false;
@@ -515,6 +591,24 @@ int apply_outlet_marks(wdpm_solver* s, bool on) {
     return WDPM_OK;
 }
 
+// After any change of the water grid from outside (upload, copy, quantise): nothing is known about signs until the
+// next block prologue; whether invalid cells are dry is established here (one pass, the callers synchronise anyway).
+int refresh_water_flags(wdpm_solver* s) {
+    s->water_clean = false;
+    const long long n = s->g.cells_dev();
+    const int grid = grid_for(n, 256, s->sm_count);
+    CUDA_TRY(cudaMemsetAsync(s->d_dirty, 0, sizeof(int), s->stream));
+    if (s->dtype == WDPM_F64) k_check_invalid_water<double><<<grid, 256, 0, s->stream>>>(static_cast<const double*>(s->w[s->cur]), static_cast<const double*>(s->dem), n, s->d_dirty);
+    else k_check_invalid_water<float><<<grid, 256, 0, s->stream>>>(static_cast<const float*>(s->w[s->cur]), static_cast<const float*>(s->dem), n, s->d_dirty);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    int dirty = 1;
+    CUDA_TRY(cudaMemcpyAsync(&dirty, s->d_dirty, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->invalid_dry = dirty == 0;
+    return WDPM_OK;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------
@@ -595,6 +689,10 @@ int wdpm_create(const wdpm_config* cfg, wdpm_solver** out) {
     cudaError_t e = cudaGetDeviceProperties(&prop, cfg->device);
     if (e != cudaSuccess) { delete s; return fail(WDPM_E_CUDA, cudaGetErrorString(e)); }
     s->sm_count = prop.multiProcessorCount;
+    if (const char* t = getenv("WDPM_B200_HALO_TIMEOUT_MS")) {
+        const double ms = atof(t);
+        if (ms > 0) s->halo_timeout_ns = (unsigned long long)(ms * 1e6);
+    }
 
     // kernel + variant
     const long long cells = (long long)(cfg->rows + 2) * (cfg->cols + 2);
@@ -607,7 +705,8 @@ int wdpm_create(const wdpm_config* cfg, wdpm_solver** out) {
     int variant = cfg->fused_variant;
     if (variant < 0 || variant > nvar) { delete s; return fail(WDPM_E_ARG, "fused_variant out of range"); }
     if (variant == 0) {
-        variant = s->dtype == WDPM_F64 ? (cfg->module == WDPM_DRAIN ? kDefaultVariantF64Drain : kDefaultVariantF64) : kDefaultVariantF32;
+        variant = s->dtype == WDPM_F64 ? (cfg->module == WDPM_DRAIN ? kDefaultVariantF64Drain : kDefaultVariantF64)
+                                       : (cfg->module == WDPM_DRAIN ? kDefaultVariantF32Drain : kDefaultVariantF32);
         // Drain's folded-gate step needs water that is never -0.0: guaranteed by a zero threshold > 0 (relax.cuh)
         if (s->dtype == WDPM_F64 && cfg->module == WDPM_DRAIN && cfg->zero_threshold > 0.0) variant = kDefaultVariantF64DrainFast;
         if (cells < kSmallGridCells && !is_stripe) variant = s->dtype == WDPM_F64 ? kSmallGridVariantF64 : kSmallGridVariantF32;
@@ -630,6 +729,11 @@ int wdpm_create(const wdpm_config* cfg, wdpm_solver** out) {
     } else {
         const auto& v = fused_variants<float>()[s->variant];
         W = v.W; TWV = v.TWV; HL = v.HL; K = v.K; NT = v.NT; minb = v.minb; prepare = v.prepare;
+    }
+    {
+        const bool has_module = s->dtype == WDPM_F64 ? fused_variants<double>()[s->variant].launch[s->module] != nullptr
+                                                     : fused_variants<float>()[s->variant].launch[s->module] != nullptr;
+        if (!has_module) { delete s; return fail(WDPM_E_UNSUPPORTED, "this fused variant does not implement the module (warp-autonomous variants: Add and Subtract)"); }
     }
     if (s->kernel == WDPM_KERNEL_FUSED) {
         e = prepare();
@@ -705,7 +809,9 @@ int wdpm_create(const wdpm_config* cfg, wdpm_solver** out) {
         (e = cudaMalloc((void**)&s->d_result, sizeof(BlockPartial))) != cudaSuccess ||
         (e = cudaMalloc((void**)&s->outlet_partials, sizeof(OutletCand) * s->reduce_blocks)) != cudaSuccess ||
         (e = cudaMalloc((void**)&s->d_outlet, sizeof(OutletCand))) != cudaSuccess ||
-        (e = cudaHostAlloc((void**)&s->h_result, sizeof(BlockPartial), cudaHostAllocDefault)) != cudaSuccess)
+        (e = cudaMalloc((void**)&s->d_dirty, sizeof(int))) != cudaSuccess ||
+        (e = cudaHostAlloc((void**)&s->h_result, sizeof(BlockPartial), cudaHostAllocDefault)) != cudaSuccess ||
+        (e = cudaHostAlloc((void**)&s->h_halo_error, sizeof(int), cudaHostAllocDefault)) != cudaSuccess)
         return cleanup(WDPM_E_NOMEM, std::string("cudaMalloc scratch: ") + cudaGetErrorString(e));
     if ((e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
         return cleanup(WDPM_E_CUDA, cudaGetErrorString(e));
@@ -738,10 +844,11 @@ int wdpm_destroy(wdpm_solver* s) {
             cudaIpcCloseMemHandle(peer->flags);
         }
     if (s->flags) cudaFree(s->flags);
-    void* ptrs[] = {s->dem, s->w[0], s->w[1], s->oldw, s->totaldrain, s->events, s->saved_elev, s->d_outlet_rc, s->partials, s->d_result, s->outlet_partials, s->d_outlet};
+    void* ptrs[] = {s->dem, s->w[0], s->w[1], s->oldw, s->totaldrain, s->events, s->saved_elev, s->d_outlet_rc, s->partials, s->d_result, s->outlet_partials, s->d_outlet, s->d_dirty};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->h_result) cudaFreeHost(s->h_result);
+    if (s->h_halo_error) cudaFreeHost(s->h_halo_error);
     for (auto& evn : s->ev)
         if (evn) cudaEventDestroy(evn);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
@@ -797,8 +904,7 @@ int wdpm_upload_water(wdpm_solver* s, const void* water) {
     } else {
         CUDA_TRY(cudaMemsetAsync(s->w[s->cur], 0, (size_t)s->g.cells_dev() * s->esize, s->stream));
     }
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
-    return WDPM_OK;
+    return refresh_water_flags(s);
 }
 
 int wdpm_download_water(wdpm_solver* s, void* water) {
@@ -831,6 +937,7 @@ int wdpm_apply_add(wdpm_solver* s, double depth, double runoff_fraction) {
     else
         k_apply_add<float><<<grid, 256, 0, s->stream>>>(static_cast<float*>(s->w[s->cur]), static_cast<const float*>(s->dem), n,
                                                         (float)depth, (float)(depth * runoff_fraction));
+    s->water_clean = false;
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     return WDPM_OK;
@@ -848,6 +955,7 @@ int wdpm_apply_subtract(wdpm_solver* s, double depth) {
     else
         k_apply_subtract<float><<<grid, 256, 0, s->stream>>>(static_cast<float*>(s->w[s->cur]), static_cast<const float*>(s->dem), n,
                                                              (float)depth);
+    s->water_clean = false;
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     return WDPM_OK;
@@ -962,6 +1070,7 @@ int wdpm_quantize_water(wdpm_solver* s) {
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->water_clean = false;
     return WDPM_OK;
 }
 
@@ -1000,7 +1109,7 @@ int wdpm_copy_state(wdpm_solver* dst, wdpm_solver* src, int32_t what) {
     }
     CUDA_TRY(cudaStreamSynchronize(dst->stream));
     CUDA_TRY(cudaStreamSynchronize(src->stream));
-    return WDPM_OK;
+    return (what & WDPM_COPY_WATER) ? refresh_water_flags(dst) : WDPM_OK;
 }
 
 int wdpm_get_cell_water(wdpm_solver* s, int32_t row, int32_t col, double* value) {
@@ -1018,8 +1127,33 @@ int wdpm_get_cell_water(wdpm_solver* s, int32_t row, int32_t col, double* value)
     return WDPM_OK;
 }
 
+int wdpm_water_checksum(wdpm_solver* s, uint64_t* checksum) {
+    if (!s || !checksum) return fail(WDPM_E_ARG, "null argument");
+    if (!s->have_dem) return fail(WDPM_E_STATE, "nothing uploaded yet");
+    CUDA_TRY(cudaSetDevice(s->device));
+    // owned interior rows in local padded coordinates (a stripe's first/last padded row may be the DEM's halo ring)
+    const int lo = s->stripe ? std::max(s->G, 1) - s->G : 1;
+    const int hi = s->stripe ? std::min(s->G + s->P, s->cfg.rows + 1) - s->G : s->g.R + 1;
+    unsigned long long* d_sum = reinterpret_cast<unsigned long long*>(s->partials);  // scratch, free between blocks
+    if (s->in_block) return fail(WDPM_E_STATE, "a block is open");
+    CUDA_TRY(cudaMemsetAsync(d_sum, 0, sizeof(unsigned long long), s->stream));
+    const int grid = std::max(1, std::min(hi - lo, s->sm_count * 8));
+    if (s->dtype == WDPM_F64)
+        k_water_checksum<double><<<grid, 256, 0, s->stream>>>(static_cast<const double*>(s->w[s->cur]), s->g, lo, hi - lo, s->G, s->cfg.cols, d_sum);
+    else
+        k_water_checksum<float><<<grid, 256, 0, s->stream>>>(static_cast<const float*>(s->w[s->cur]), s->g, lo, hi - lo, s->G, s->cfg.cols, d_sum);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long v = 0;
+    CUDA_TRY(cudaMemcpyAsync(&v, d_sum, sizeof(v), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    *checksum = (uint64_t)v;
+    return WDPM_OK;
+}
+
 int wdpm_run_block(wdpm_solver* s, int32_t n_iters, wdpm_block_result* out) {
     if (!s) return fail(WDPM_E_ARG, "null solver");
+    if (s->halo_failed) return fail(WDPM_E_HALO, "an earlier halo wait timed out: upload again");
     if (n_iters < 0) return fail(WDPM_E_ARG, "negative iteration count");
     if (!s->have_dem) return fail(WDPM_E_STATE, "upload first");
     if (s->module == WDPM_DRAIN && !s->have_outlet) return fail(WDPM_E_STATE, "Drain needs an outlet: call wdpm_find_outlet or wdpm_set_outlet");
@@ -1029,6 +1163,7 @@ int wdpm_run_block(wdpm_solver* s, int32_t n_iters, wdpm_block_result* out) {
 
 int wdpm_block_begin(wdpm_solver* s) {
     if (!s) return fail(WDPM_E_ARG, "null solver");
+    if (s->halo_failed) return fail(WDPM_E_HALO, "an earlier halo wait timed out: upload again");
     if (!s->have_dem) return fail(WDPM_E_STATE, "upload first");
     if (s->in_block) return fail(WDPM_E_STATE, "a block is already open");
     if (s->module == WDPM_DRAIN && !s->have_outlet) return fail(WDPM_E_STATE, "Drain needs an outlet: call wdpm_find_outlet or wdpm_set_outlet");
@@ -1055,6 +1190,7 @@ int wdpm_block_end(wdpm_solver* s, wdpm_block_result* out) {
 
 int wdpm_iterate(wdpm_solver* s, int32_t n_iters) {
     if (!s) return fail(WDPM_E_ARG, "null solver");
+    if (s->halo_failed) return fail(WDPM_E_HALO, "an earlier halo wait timed out: upload again");
     if (n_iters < 0) return fail(WDPM_E_ARG, "negative iteration count");
     if (!s->have_dem) return fail(WDPM_E_STATE, "upload first");
     if (s->module == WDPM_DRAIN && !s->have_outlet) return fail(WDPM_E_STATE, "Drain needs an outlet");
@@ -1077,9 +1213,10 @@ int wdpm_get_info(wdpm_solver* s, wdpm_info* info) {
     info->kernel_launches = s->launches;
     info->kernel = s->kernel;
     info->sm_count = s->sm_count;
-    int W, TWV, K, nt; size_t smem;
-    if (s->dtype == WDPM_F64) { const auto& v = fused_variants<double>()[s->variant]; W = v.W; TWV = v.TWV; K = v.K; nt = v.nthreads; smem = v.smem; }
-    else { const auto& v = fused_variants<float>()[s->variant]; W = v.W; TWV = v.TWV; K = v.K; nt = v.nthreads; smem = v.smem; }
+    int W, TWV, K, nt; size_t smem; bool wa;
+    if (s->dtype == WDPM_F64) { const auto& v = fused_variants<double>()[s->variant]; W = v.W; TWV = v.TWV; K = v.K; nt = v.nthreads; smem = v.smem; wa = v.wa; }
+    else { const auto& v = fused_variants<float>()[s->variant]; W = v.W; TWV = v.TWV; K = v.K; nt = v.nthreads; smem = v.smem; wa = v.wa; }
+    info->warp_autonomous = (s->kernel == WDPM_KERNEL_FUSED && wa) ? 1 : 0;
     info->strip_cols = TWV;
     info->window_cols = W;
     info->chunk_rows = 3 * s->chunk_triples;
@@ -1144,14 +1281,15 @@ int wdpm_stripe_upload(wdpm_solver* s, const void* dem_band, const void* water_b
                                    s->stream));
     CUDA_TRY(cudaMemsetAsync(s->flags, 0, sizeof(HaloFlags), s->stream));
     s->epoch = 0;
+    s->halo_failed = false;
+    *s->h_halo_error = 0;
     s->have_dem = true;
     s->marks_applied = false;  // the upload replaced the marked cells
     {
         const int rc = apply_outlet_marks(s, true);
         if (rc) return rc;
     }
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
-    return WDPM_OK;
+    return refresh_water_flags(s);
 }
 
 int wdpm_stripe_export(wdpm_solver* s, wdpm_stripe_endpoint* self) {
@@ -1227,6 +1365,14 @@ int wdpm_stripe_phase(wdpm_solver* s, int32_t phase) {
     if (phase == 1) return WDPM_OK;  // the iteration kernel has already exported the halo rows
     return fail(WDPM_E_ARG, "phase must be 0 or 1");
 }
+
+#ifdef WDPM_TEST_HOOKS
+int wdpm_debug_counters(int32_t* out4) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyFromSymbol(out4, g_dbg_counters, sizeof(int) * 4));
+    return WDPM_OK;
+}
+#endif
 
 #ifdef WDPM_TIMELINE
 // Developer probe (scripts/timeline.py builds a separate library with -DWDPM_TIMELINE).

@@ -19,7 +19,9 @@ KERNEL_AUTO, KERNEL_COLOUR, KERNEL_FUSED, KERNEL_RESIDENT = 0, 1, 2, 3
 MODULES = {"add": ADD, "subtract": SUBTRACT, "drain": DRAIN}
 # the tiling AUTO picks for large fp64 Add/Subtract grids (kDefaultVariantF64 in csrc/solver.cu); tests and
 # smoke() name it to exercise the production kernel on small grids
-PRODUCTION_FUSED_VARIANT_F64 = 13
+PRODUCTION_FUSED_VARIANT_F64 = 17   # warp-autonomous kernel (k_fused_wa), Add / Subtract
+PRODUCTION_FUSED_VARIANT_F32 = 16
+PRODUCTION_FUSED_VARIANT_F64_DRAIN = 15  # k_fused with the folded-gate Drain step (zero threshold > 0)
 
 _PKG = Path(__file__).resolve().parent
 
@@ -48,7 +50,7 @@ class _Info(C.Structure):
     _fields_ = [("device_bytes", C.c_int64), ("kernel_launches", C.c_int64), ("kernel", C.c_int32),
                 ("strip_cols", C.c_int32), ("window_cols", C.c_int32), ("chunk_rows", C.c_int32),
                 ("grid_ctas", C.c_int32), ("cta_threads", C.c_int32), ("smem_bytes", C.c_int32),
-                ("iters_per_launch", C.c_int32), ("sm_count", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("iters_per_launch", C.c_int32), ("sm_count", C.c_int32), ("warp_autonomous", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
 @dataclasses.dataclass
@@ -219,10 +221,28 @@ class Solver:
         _check(self._lib.wdpm_get_cell_water(self._h, C.c_int32(row), C.c_int32(col), C.byref(v)))
         return v.value
 
+    def water_checksum(self) -> int:
+        """Order-free 64-bit checksum of the owned interior water cells (position-weighted bit patterns, mod 2^64)."""
+        v = C.c_uint64()
+        _check(self._lib.wdpm_water_checksum(self._h, C.byref(v)))
+        return int(v.value)
+
     # -- the hot path -----------------------------------------------------
     def run_block(self, n_iters: int = 1000) -> BlockResult:
         r = _BlockResult()
         _check(self._lib.wdpm_run_block(self._h, C.c_int32(n_iters), C.byref(r)))
+        return BlockResult(r.max_diff, r.masked_sum, r.total_drain, r.wet_cells, r.iterations, r.launches, r.block_ms, r.iterate_ms)
+
+    def block_begin(self):
+        """Threshold + snapshot, non-blocking (hosts that feed several stripe solvers round-robin)."""
+        _check(self._lib.wdpm_block_begin(self._h))
+
+    def block_enqueue(self, n_iters: int):
+        _check(self._lib.wdpm_block_enqueue(self._h, C.c_int32(n_iters)))
+
+    def block_end(self) -> BlockResult:
+        r = _BlockResult()
+        _check(self._lib.wdpm_block_end(self._h, C.byref(r)))
         return BlockResult(r.max_diff, r.masked_sum, r.total_drain, r.wet_cells, r.iterations, r.launches, r.block_ms, r.iterate_ms)
 
     def iterate(self, n_iters: int):
