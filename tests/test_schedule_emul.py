@@ -132,11 +132,11 @@ def test_wa_schedule_is_bit_exact(oracle, emul, cfg, dt):
 
 
 def test_wa_unguarded_add_on_a_clean_grid(oracle, emul):
-    """No activity test at all (fp64 Add, kOptNoGuard): exact as long as the water is +0 wherever the reference
+    """No activity test at all (Add with the cap-free steps, kOptNoGuard): exact as long as the water is +0 wherever the reference
     skips the centre - dry cells, NODATA cells and the halo ring included - which is what the solver checks."""
     rng = np.random.default_rng(41)
-    for cfg, rows, cols, ct in ((0, 40, 300, 5), (1, 33, 420, 0)):
-        D, Wt = random_case(rng, rows, cols, np.float64, wet_fraction=0.5, nodata_fraction=0.15)
+    for cfg, rows, cols, ct, dt in ((0, 40, 300, 5, np.float64), (1, 33, 420, 0, np.float64), (0, 40, 300, 5, np.float32), (3, 20, 700, 0, np.float32)):
+        D, Wt = random_case(rng, rows, cols, dt, wet_fraction=0.5, nodata_fraction=0.15)
         assert not np.signbit(Wt).any() and not Wt[D <= -99999.0].any()
         a, b = Wt.copy(), Wt.copy()
         oracle.iterate(a, D, -99999.0, po.ADD, 4)

@@ -919,8 +919,8 @@ __device__ __forceinline__ T shfl_from_right(T v) {
     return __shfl_down_sync(0xffffffffu, v, 1);
 }
 
-template <typename T, int MODULE, typename CFG, int OPT>
-__global__ void __launch_bounds__(CFG::NWARPS * 32 + fused_extra_threads(OPT), 1)
+template <typename T, int MODULE, typename CFG, int OPT, int MINB = 1>
+__global__ void __launch_bounds__(CFG::NWARPS * 32 + fused_extra_threads(OPT), MINB)
 k_fused_wa(const FusedParams<T> p) {
     constexpr int NTHREADS = CFG::NWARPS * 32;
     constexpr int NALL = NTHREADS + fused_extra_threads(OPT);
@@ -928,9 +928,9 @@ k_fused_wa(const FusedParams<T> p) {
     constexpr int kLaunchRegs = (65536 / NALL) & ~7;
     constexpr int kComputeRegsRaw = ((kLaunchRegs * NALL - 128 * 24) / NTHREADS) & ~7;
     constexpr int kComputeRegs = kComputeRegsRaw > 232 ? 232 : kComputeRegsRaw;
-    static_assert(!REALLOC || (NTHREADS % 128 == 0 && kComputeRegs > kLaunchRegs), "register reallocation needs whole warp groups");
+    static_assert(!REALLOC || (MINB == 1 && NTHREADS % 128 == 0 && kComputeRegs > kLaunchRegs), "register reallocation needs whole warp groups, one CTA per SM");
     constexpr int W = CFG::W, NT = CFG::NT, NPH = CFG::NPH, NRING = CFG::NRING, NSTAGE = CFG::NSTAGE, KW = CFG::KW;
-    constexpr bool FAST = sizeof(T) == 8 && (OPT & kOptAddFast) && MODULE == kAdd;
+    constexpr bool FAST = (OPT & kOptAddFast) && MODULE == kAdd;  // fp64: push_add_fast, fp32: push_add_nocap
     constexpr bool GUARD = !(FAST && (OPT & kOptNoGuard));
     using V2 = typename Vec2<T>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -973,7 +973,9 @@ k_fused_wa(const FusedParams<T> p) {
     for (int s = 0; s < tile.n_steps; s++) {
         const int m = tile.m_lo + NT * s - ph * CFG::LAG + t;
         const bool run = tile.runnable(m, ph);
+        WDPM_TL(0);
         if (ph == 0 && step_has_loads<CFG>(tile, s)) mbar_wait(&bars[s % NSTAGE], (uint32_t)((s / NSTAGE) & 1));
+        WDPM_TL(1);
         if (run) {
             const int row0 = 3 * m + ph;
             int s0 = tile.ring_slot(row0);
@@ -995,17 +997,21 @@ k_fused_wa(const FusedParams<T> p) {
                 }
             }
             wa_relax_pair<T, MODULE, 0, FAST, GUARD>(wt, dd);
+            WDPM_TL(2);
             // every lane's window is in registers (the relax above consumed it): tell the row group
             __syncwarp();
             if (lane == 0) mbar_arrive(gbar);
 #pragma unroll
             for (int r = 0; r < 3; r++) wt[r][6] = shfl_from_right(wt[r][0]);
             wa_relax_pair<T, MODULE, 1, FAST, GUARD>(wt, dd);
+            WDPM_TL(3);
 #pragma unroll
             for (int r = 0; r < 3; r++) wt[r][7] = shfl_from_right(wt[r][1]);
             wa_relax_pair<T, MODULE, 2, FAST, GUARD>(wt, dd);
+            WDPM_TL(4);
             // the neighbouring warps of this row triple read columns I am about to overwrite: they must hold them by now
             if (KW > 1) mbar_wait(gbar, (uint32_t)(s & 1));
+            WDPM_TL(5);
             if (stores) {
 #pragma unroll
                 for (int r = 0; r < 3; r++) {
@@ -1021,7 +1027,9 @@ k_fused_wa(const FusedParams<T> p) {
             if (lane == 0) mbar_arrive(gbar);  // keep the group barrier's phase in step with s
         }
         fence_proxy_async();  // make this step's smem writes visible to the bulk-store engine
+        WDPM_TL(7);
         __syncthreads();
+        WDPM_TL(8);
     }
 }
 

@@ -95,35 +95,35 @@ FusedVariant<T> make_variant() {
 }
 
 // Warp-autonomous variants (kernels.cuh, k_fused_wa): Add and Subtract only.
-template <typename T, int MODULE, typename CFG, int OPT>
+template <typename T, int MODULE, typename CFG, int OPT, int MINB>
 cudaError_t launch_wa(const FusedParams<T>& p, int grid, cudaStream_t st) {
-    k_fused_wa<T, MODULE, CFG, OPT><<<grid, CFG::NWARPS * 32 + fused_extra_threads(OPT), wa_smem_bytes<CFG, T>(), st>>>(p);
+    k_fused_wa<T, MODULE, CFG, OPT, MINB><<<grid, CFG::NWARPS * 32 + fused_extra_threads(OPT), wa_smem_bytes<CFG, T>(), st>>>(p);
     return cudaGetLastError();
 }
 
-template <typename T, typename CFG, int OPT>
+template <typename T, typename CFG, int OPT, int MINB>
 cudaError_t prepare_wa() {
     const int smem = (int)wa_smem_bytes<CFG, T>();
     cudaError_t e;
-    e = cudaFuncSetAttribute(k_fused_wa<T, kAdd, CFG, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = cudaFuncSetAttribute(k_fused_wa<T, kAdd, CFG, OPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_fused_wa<T, kAdd, CFG, OPT | kOptNoGuard>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = cudaFuncSetAttribute(k_fused_wa<T, kAdd, CFG, OPT | kOptNoGuard, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_fused_wa<T, kSubtract, CFG, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    return cudaFuncSetAttribute(k_fused_wa<T, kSubtract, CFG, OPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
-template <typename T, typename CFG, int OPT = 0>
+template <typename T, typename CFG, int OPT = 0, int MINB = 1>
 FusedVariant<T> make_wa_variant() {
     FusedVariant<T> v;
     v.W = CFG::W; v.TWV = CFG::TWV; v.HL = CFG::HL; v.K = CFG::K; v.NT = CFG::NT; v.PF = CFG::PF;
-    v.nthreads = CFG::NWARPS * 32; v.minb = 1; v.wa = true;
+    v.nthreads = CFG::NWARPS * 32; v.minb = MINB; v.wa = true;
     v.smem = wa_smem_bytes<CFG, T>();
-    v.launch[kAdd] = launch_wa<T, kAdd, CFG, OPT>;
-    v.launch[kSubtract] = launch_wa<T, kSubtract, CFG, OPT>;
+    v.launch[kAdd] = launch_wa<T, kAdd, CFG, OPT, MINB>;
+    v.launch[kSubtract] = launch_wa<T, kSubtract, CFG, OPT, MINB>;
     v.launch[kDrain] = nullptr;
-    v.launch_clean[kAdd] = (sizeof(T) == 8 && (OPT & kOptAddFast)) ? launch_wa<T, kAdd, CFG, OPT | kOptNoGuard> : nullptr;
+    v.launch_clean[kAdd] = (OPT & kOptAddFast) ? launch_wa<T, kAdd, CFG, OPT | kOptNoGuard, MINB> : nullptr;
     v.launch_clean[kSubtract] = v.launch_clean[kDrain] = nullptr;
-    v.prepare = prepare_wa<T, CFG, OPT>;
+    v.prepare = prepare_wa<T, CFG, OPT, MINB>;
     return v;
 }
 
@@ -177,8 +177,11 @@ const std::vector<FusedVariant<float>>& fused_variants<float>() {
         make_variant<float, MwCfg<484, 1, 1, 2>, 480, 2>(),    // 12: 160 tiles per row group, two CTAs per SM
         make_variant<float, MwCfg<772, 2, 1, 1>, 768, 1>(),    // 13: 256 tiles per row group... one CTA per SM
         make_wa_variant<float, WaCfg<2, 2, 1>, kOptRegRealloc>(),  // 14: warp-autonomous, 12 warps x 2 tiles per lane
-        make_wa_variant<float, WaCfg<1, 1, 1>>(),                  // 15: test window for 14
-        make_wa_variant<float, WaCfg<4, 2, 1>, kOptRegRealloc>(),  // 16: 752-column window, 24 warps
+        make_wa_variant<float, WaCfg<1, 1, 1>, kOptAddFast>(),     // 15: test window for 16
+        make_wa_variant<float, WaCfg<4, 2, 1>, kOptAddFast | kOptRegRealloc>(),  // 16: 752-column window, 24 warps, cap-free Add step
+        make_wa_variant<float, WaCfg<2, 2, 1>, kOptAddFast, 2>(),  // 17: as 14, two CTAs per SM
+        make_wa_variant<float, WaCfg<3, 2, 1>, kOptAddFast>(),     // 18: 566-column window, 18 warps
+        make_wa_variant<float, WaCfg<4, 2, 1>, kOptRegRealloc>(),  // 19: as 16 with the reference form of the step (comparison)
     };
     return v;
 }
