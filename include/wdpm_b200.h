@@ -131,7 +131,10 @@ int wdpm_set_outlet(wdpm_solver *s, int32_t drainrow, int32_t draincol);
  * coordinates of the whole DEM. Each outlet follows src/runoff.cl:104-111 - never a centre; a
  * neighbouring centre empties itself and the outlet into that outlet's total. One outlet is the
  * reference. Every outlet has its own accumulator; the reported total is their sum in outlet order
- * (solver precision). Replaces any earlier set. Drain solvers only. */
+ * (solver precision). Replaces any earlier set. Drain solvers only. Row stripes: every stripe is given the whole
+ * set; an outlet's total is kept by the stripe that owns its row - contacts from centres of a neighbouring stripe
+ * are recorded there too, in sub-pass order, so each total is bit-identical to the single-GPU one - and reads as 0 on
+ * the other stripes: a host adds the stripes' wdpm_get_outlet_drains element by element. */
 #define WDPM_MAX_OUTLETS 1024
 int wdpm_set_outlets(wdpm_solver *s, int32_t n, const int32_t *rows, const int32_t *cols);
 int wdpm_get_outlet_drains(wdpm_solver *s, double *values, int32_t n);
@@ -247,11 +250,12 @@ int wdpm_stripe_band(wdpm_solver *s, int32_t *band_row0, int32_t *band_rows, int
                      int32_t *owned_rows);
 int wdpm_stripe_upload(wdpm_solver *s, const void *dem_band, const void *water_band,
                        int32_t band_row0, int32_t band_rows);
-/* One iteration without the wait for the neighbours' halos, for hosts that drive several
- * in-process stripes in lockstep on one GPU (tests): phase 0 = launch the iteration kernel, which
- * also writes this stripe's halo rows into the neighbours' buffers and raises their flags; phase 1
- * is accepted and does nothing (the halo push used to be a kernel of its own).
- * wdpm_iterate / wdpm_run_block do wait + compute/push per iteration on their own. */
+/* One iteration without the wait for the neighbours' halos, for hosts that drive several in-process stripes in
+ * lockstep (tests): phase 0 = launch the iteration kernel, which also writes this stripe's halo rows into the
+ * neighbours' buffers and raises their flags; phase 1, to be called once EVERY stripe has completed phase 0, folds
+ * the Drain contacts of that iteration into the outlets' totals (a neighbour records the contacts of its centres
+ * with this stripe's outlets in this stripe's buffers; a no-op for Add / Subtract).
+ * wdpm_iterate / wdpm_run_block do all of it per iteration on their own. */
 int wdpm_stripe_phase(wdpm_solver *s, int32_t phase);
 
 #ifdef __cplusplus

@@ -75,7 +75,17 @@ allc = [None] * world
 dist.all_gather_object(allc, cand)
 best = min((c for c in allc if c is not None), key=lambda c: (c[2], c[0], c[1]))
 assert best[2] == gmin and (best[0] - 1) * n + (best[1] - 1) == gpos, (best, gmin, gpos)
-outlets = [(best[0], best[1])] + [rc for rc in rim if rc != (best[0], best[1])][: a.outlets - 1]
+# rim cells ON the stripe borders of an 8-way partition (left column at a stripe's first row, right column at the row
+# above it): their neighbouring centres belong to two stripes at 8 GPUs and to one at 2 - the case that used to make a
+# total depend on the partition
+forced = []
+if a.outlets >= 32:
+    for p8 in plan_stripes(n, 8)[1:]:
+        forced += [(p8.row0, 1), (p8.row0 - 1, n)]
+outlets = [(best[0], best[1])]
+for rc in forced + rim:
+    if rc not in outlets and len(outlets) < a.outlets:
+        outlets.append(rc)
 ds.solver.set_outlets(outlets)
 owner = st.row0 <= best[0] < st.row0 + st.rows
 w_out = ds.solver.get_cell_water(best[0], best[1]) if owner else 0.0
@@ -94,11 +104,20 @@ for b in range(a.blocks):
     if rank == 0:
         print(json.dumps(lines[-1]), flush=True)
     assert abs(bal) < (1e-9 if a.thres_mm == 0 else 1e-5), bal
+# what must not depend on the number of GPUs: the water grid (order-free checksum) and every outlet's total (bit patterns)
+per_outlet = ds.outlet_drains(len(outlets))
+checksum = ds.solver.water_checksum()
+parts = [None] * world
+dist.all_gather_object(parts, checksum)
+checksum = sum(parts) % (1 << 64)
 if rank == 0:
     info = ds.solver.info()
     summary = {"size": n, "gpus": world, "dtype": "f64", "module": "drain", "outlet": [best[0], best[1]], "min_elevation": best[2],
                "n_outlets": len(outlets), "outlets_head": outlets[:8],
-               "setup_s": t_setup, "device_bytes_per_gpu": info["device_bytes"], "blocks": lines}
+               "setup_s": t_setup, "device_bytes_per_gpu": info["device_bytes"], "blocks": lines,
+               "water_checksum": f"{checksum:016x}", "outlet_totals_bits": [f"{int(np.float64(v).view(np.uint64)):016x}" for v in per_outlet],
+               "outlet_totals_m": [float(v) for v in per_outlet],
+               "outlets_on_stripe_borders": [list(o) for o in outlets if any(abs(o[0] - p.row0) <= 1 for p in plan_stripes(n, world)[1:])]}
     print(json.dumps(summary))
     if a.out:
         Path(a.out).write_text(json.dumps(summary, indent=1))

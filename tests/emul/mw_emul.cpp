@@ -17,6 +17,7 @@
 // Nothing under wdpm_b200/ links against this file.
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <vector>
@@ -299,8 +300,164 @@ void run_cta_wa(const Layout& L, const T* w_in, T* w_out, const T* dem, int stri
     wait_read(0);
 }
 
+// The STAGGERED order of k_fused_wa (kOptStagger, NT = 2): half steps; slot-0 groups begin step h/2 at even h and
+// end it at odd h, slot-1 groups half a step later; rows are written home half a step after they are finished,
+// slot 0 and slot 1 in store groups of their own. Windows live in "registers" (Lane) between the halves, so a
+// ring slot that is reloaded or overwritten in between shows up as a wrong row at write-back.
 template <typename T, int MODULE, typename CFG, bool FAST, bool GUARD>
-int run_launches_wa(T* w_padded, const T* d_padded, int R, int C, T nodata, int n_launches, int chunk_triples, long long* err_out) {
+void run_cta_wa_stag(const Layout& L, const T* w_in, T* w_out, const T* dem, int strip, int chunk,
+                     int chunk_triples, int total_triples, Errors& err, std::vector<unsigned char>& stored_mask) {
+    constexpr int W = CFG::W, NT = CFG::NT, NPH = CFG::NPH, NRING = CFG::NRING, PF = CFG::PF, KW = CFG::KW;
+    static_assert(NT == 2, "staggered schedule");
+    MwTile<CFG> tile;
+    tile.init(strip, chunk, chunk_triples, total_triples);
+    std::vector<T> ring_w((size_t)NRING * W), ring_d((size_t)NRING * W);
+    std::vector<int> slot_row(NRING, INT32_MIN);
+    std::deque<std::vector<int>> groups;
+    std::vector<int> slot_pending(NRING, 0);
+    const int col0 = tile.x0 + kPadLeft;
+    const int n = tile.n_steps;
+
+    // everything inside a half step runs concurrently on the GPU: two parties (row groups, the copy engine) touching
+    // the same ring slot in the same half step is a race
+    std::vector<int> claim_h(NRING, -2), claim_who(NRING, -1);
+    int cur_h = -1;
+    auto claim = [&](int slot, int who) {
+        if (claim_h[slot] == cur_h && claim_who[slot] != who) {
+            err.wrong_row++;
+            if (getenv("WDPM_EMUL_DEBUG")) fprintf(stderr, "claim conflict: half step %d slot %d row %d: %d vs %d\n", cur_h, slot, slot_row[slot], claim_who[slot], who);
+        }
+        claim_h[slot] = cur_h;
+        claim_who[slot] = who;
+    };
+
+    auto issue_loads = [&](int s) {
+        for (int t = 0; t < NT; t++) {
+            const int m = tile.triple(s, 0, t);
+            if (!tile.staged(m)) continue;
+            for (int k = 0; k < 3; k++) {
+                const int row = 3 * m + k;
+                const int slot = tile.ring_slot(row);
+                if (slot_pending[slot]) err.load_over_store++;
+                claim(slot, 100);
+                const size_t src = (size_t)(row + kPadTop) * L.pitch + col0;
+                std::memcpy(&ring_w[(size_t)slot * W], w_in + src, W * sizeof(T));
+                std::memcpy(&ring_d[(size_t)slot * W], dem + src, W * sizeof(T));
+                slot_row[slot] = row;
+            }
+        }
+    };
+    auto issue_stores = [&](int s, int t) {
+        std::vector<int> grp;
+        const int m = tile.triple(s, NPH - 1, t);
+        for (int k = 0; k < 3; k++) {
+            const int row = 3 * m + 2 + k;
+            if (!tile.owns_row(row)) continue;
+            const int slot = tile.ring_slot(row);
+            if (slot_row[slot] != row) err.wrong_row++;
+            claim(slot, 101);
+            const size_t dst = (size_t)(row + kPadTop) * L.pitch + col0 + CFG::HL;
+            std::memcpy(w_out + dst, &ring_w[(size_t)slot * W + CFG::HL], CFG::TWV * sizeof(T));
+            for (int c = 0; c < CFG::TWV; c++) {
+                if (stored_mask[dst + c]) err.double_store++;
+                stored_mask[dst + c] = 1;
+            }
+            grp.push_back(slot);
+            slot_pending[slot]++;
+        }
+        if (!grp.empty()) groups.push_back(grp);
+    };
+    auto wait_read = [&](size_t allowed) {
+        while (groups.size() > allowed) {
+            for (int slot : groups.front()) slot_pending[slot]--;
+            groups.pop_front();
+        }
+    };
+    struct Lane { T wt[3][8], dd[3][8]; };
+    struct Group { std::vector<Lane> lanes; bool run = false; int sl[3] = {0, 0, 0}; int row0 = 0; };
+    std::vector<Group> gs(NPH * NT);
+    for (auto& g : gs) g.lanes.resize((size_t)KW * 32);
+    auto begin_step = [&](Group& g, int ph, int t, int s) {
+        const int m = tile.triple(s, ph, t);
+        g.run = tile.runnable(m, ph);
+        if (!g.run) return;
+        g.row0 = 3 * m + ph;
+        g.sl[0] = tile.ring_slot(g.row0);
+        g.sl[1] = g.sl[0] + 1 == NRING ? 0 : g.sl[0] + 1;
+        g.sl[2] = g.sl[1] + 1 == NRING ? 0 : g.sl[1] + 1;
+        for (int r = 0; r < 3; r++) {
+            claim(g.sl[r], ph * NT + t);
+            if (slot_pending[g.sl[r]]) err.load_over_store++;  // a row whose write-back is still reading it
+        }
+        for (int r = 0; r < 3; r++)
+            if (slot_row[g.sl[r]] != g.row0 + r) err.wrong_row++;
+        for (int kw = 0; kw < KW; kw++)
+            for (int lane = 0; lane < 32; lane++) {
+                Lane& ln = g.lanes[(size_t)kw * 32 + lane];
+                const int cb = CFG::WSTRIDE * kw + CFG::CPL * lane;
+                for (int r = 0; r < 3; r++) {
+                    for (int c = 0; c < 6; c++) ln.wt[r][c] = ring_w[(size_t)g.sl[r] * W + cb + c];
+                    for (int c = 0; c < 8; c++) ln.dd[r][c] = ring_d[(size_t)g.sl[r] * W + cb + c];
+                    ln.wt[r][6] = ln.wt[r][7] = T(0);
+                }
+            }
+        for (int kw = 0; kw < KW; kw++) {
+            Lane* wl = &g.lanes[(size_t)kw * 32];
+            for (int lane = 0; lane < 32; lane++) wa_relax_pair<T, MODULE, 0, FAST, GUARD>(wl[lane].wt, wl[lane].dd);
+            for (int lane = 0; lane < 32; lane++)
+                for (int r = 0; r < 3; r++) wl[lane].wt[r][6] = wl[lane < 31 ? lane + 1 : lane].wt[r][0];
+            for (int lane = 0; lane < 32; lane++) wa_relax_pair<T, MODULE, 1, FAST, GUARD, 1>(wl[lane].wt, wl[lane].dd);
+        }
+    };
+    auto end_step = [&](Group& g, int who) {
+        if (!g.run) return;
+        for (int r = 0; r < 3; r++) claim(g.sl[r], who);
+        for (int kw = 0; kw < KW; kw++) {
+            Lane* wl = &g.lanes[(size_t)kw * 32];
+            for (int lane = 0; lane < 32; lane++) wa_relax_pair<T, MODULE, 1, FAST, GUARD, 2>(wl[lane].wt, wl[lane].dd);
+            for (int lane = 0; lane < 32; lane++)
+                for (int r = 0; r < 3; r++) wl[lane].wt[r][7] = wl[lane < 31 ? lane + 1 : lane].wt[r][1];
+            for (int lane = 0; lane < 32; lane++) wa_relax_pair<T, MODULE, 2, FAST, GUARD>(wl[lane].wt, wl[lane].dd);
+        }
+        for (int r = 0; r < 3; r++)
+            if (slot_row[g.sl[r]] != g.row0 + r) err.wrong_row++;  // the slot changed hands while the window was in registers
+        for (int kw = 0; kw < KW; kw++)
+            for (int lane = 0; lane < 31; lane++) {
+                const Lane& ln = g.lanes[(size_t)kw * 32 + lane];
+                const int cb = CFG::WSTRIDE * kw + CFG::CPL * lane;
+                for (int r = 0; r < 3; r++)
+                    for (int c = 2; c < 8; c++) ring_w[(size_t)g.sl[r] * W + cb + c] = ln.wt[r][c];
+            }
+    };
+
+    for (int s = 0; s < PF && s < n; s++) issue_loads(s);
+    for (int h = 0; h <= 2 * n; h++) {
+        cur_h = h;
+        {   // data-movement warp, before the compute of half step h
+            const int s = h >> 1;
+            if ((h & 1) == 0) {
+                if (s > 0) { issue_stores(s - 1, 0); wait_read(1); }
+                if (s + PF < n) issue_loads(s + PF);
+            } else if (s > 0) {
+                issue_stores(s - 1, 1);
+            }
+        }
+        for (int grp = 0; grp < NPH * NT; grp++) {
+            const int t = grp % NT, ph = grp / NT;
+            const int s = (h - t) >> 1;
+            if (((h - t) & 1) == 0) {
+                if (h >= t && s < n) begin_step(gs[grp], ph, t, s);
+            } else {
+                if (h > t && s < n) end_step(gs[grp], grp);
+            }
+        }
+    }
+    issue_stores(n - 1, 1);
+    wait_read(0);
+}
+
+template <typename T, int MODULE, typename CFG, bool FAST, bool GUARD>
+int run_launches_wa(T* w_padded, const T* d_padded, int R, int C, T nodata, int n_launches, int chunk_triples, long long* err_out, bool stag) {
     Layout L;
     L.R = R; L.C = C;
     const int n_strips = (C + 2 + CFG::TWV - 1) / CFG::TWV;
@@ -323,7 +480,12 @@ int run_launches_wa(T* w_padded, const T* d_padded, int R, int C, T nodata, int 
         std::vector<unsigned char> stored(n, 0);
         for (int chunk = 0; chunk < n_chunks; chunk++)
             for (int strip = 0; strip < n_strips; strip++)
-                run_cta_wa<T, MODULE, CFG, FAST, GUARD>(L, cur, nxt, dem.data(), strip, chunk, chunk_triples, total_triples, err, stored);
+                if constexpr (CFG::NT == 2) {
+                    if (stag) run_cta_wa_stag<T, MODULE, CFG, FAST, GUARD>(L, cur, nxt, dem.data(), strip, chunk, chunk_triples, total_triples, err, stored);
+                    else run_cta_wa<T, MODULE, CFG, FAST, GUARD>(L, cur, nxt, dem.data(), strip, chunk, chunk_triples, total_triples, err, stored);
+                } else {
+                    run_cta_wa<T, MODULE, CFG, FAST, GUARD>(L, cur, nxt, dem.data(), strip, chunk, chunk_triples, total_triples, err, stored);
+                }
         for (int i = 0; i < R + 2; i++)
             for (int j = 0; j < C + 2; j++)
                 if (!stored[L.at(i, j)]) err.unstored++;
@@ -347,13 +509,16 @@ int run_launches_wa(T* w_padded, const T* d_padded, int R, int C, T nodata, int 
     return 0;
 }
 
-// mode: bit 0 = fast Add step, bit 1 = no activity guard (fp64 Add on a clean grid only)
+// mode: bit 0 = fast Add step, bit 1 = no activity guard (Add on a clean grid only), bit 2 = staggered schedule (NT = 2)
 template <typename T, typename CFG>
 int dispatch_wa(int module, int mode, T* w, const T* d, int R, int C, T nodata, int n, int ct, long long* e) {
-    if (module == kAdd && mode == 3) return run_launches_wa<T, kAdd, CFG, true, false>(w, d, R, C, nodata, n, ct, e);
-    if (module == kAdd && mode == 1) return run_launches_wa<T, kAdd, CFG, true, true>(w, d, R, C, nodata, n, ct, e);
-    if (module == kAdd) return run_launches_wa<T, kAdd, CFG, false, true>(w, d, R, C, nodata, n, ct, e);
-    if (module == kSubtract) return run_launches_wa<T, kSubtract, CFG, false, true>(w, d, R, C, nodata, n, ct, e);
+    const bool stag = (mode & 4) != 0;
+    if (stag && CFG::NT != 2) return -3;
+    mode &= 3;
+    if (module == kAdd && mode == 3) return run_launches_wa<T, kAdd, CFG, true, false>(w, d, R, C, nodata, n, ct, e, stag);
+    if (module == kAdd && mode == 1) return run_launches_wa<T, kAdd, CFG, true, true>(w, d, R, C, nodata, n, ct, e, stag);
+    if (module == kAdd) return run_launches_wa<T, kAdd, CFG, false, true>(w, d, R, C, nodata, n, ct, e, stag);
+    if (module == kSubtract) return run_launches_wa<T, kSubtract, CFG, false, true>(w, d, R, C, nodata, n, ct, e, stag);
     return -1;
 }
 
@@ -364,6 +529,7 @@ int dispatch_wa_cfg(int cfg, int module, int mode, T* w, const T* d, int R, int 
         case 1: return dispatch_wa<T, WaCfg<2, 2, 1>>(module, mode, w, d, R, C, nodata, n, ct, e);
         case 2: return dispatch_wa<T, WaCfg<2, 1, 2>>(module, mode, w, d, R, C, nodata, n, ct, e);
         case 3: return dispatch_wa<T, WaCfg<3, 1, 1>>(module, mode, w, d, R, C, nodata, n, ct, e);
+        case 4: return dispatch_wa<T, WaCfg<1, 2, 1>>(module, mode, w, d, R, C, nodata, n, ct, e);
     }
     return -2;
 }
@@ -421,6 +587,7 @@ int wa_emul_cfg_info(int cfg, int* W, int* TWV) {
         case 1: *W = WaCfg<2, 2, 1>::W; *TWV = WaCfg<2, 2, 1>::TWV; return 0;
         case 2: *W = WaCfg<2, 1, 2>::W; *TWV = WaCfg<2, 1, 2>::TWV; return 0;
         case 3: *W = WaCfg<3, 1, 1>::W; *TWV = WaCfg<3, 1, 1>::TWV; return 0;
+        case 4: *W = WaCfg<1, 2, 1>::W; *TWV = WaCfg<1, 2, 1>::TWV; return 0;
     }
     return -1;
 }

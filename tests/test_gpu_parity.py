@@ -86,7 +86,7 @@ def _implements(variant, code, mod):
         return False
 
 
-WA_VARIANTS = {np.float64: [17, 18, 19, 20, 21], np.float32: [14, 15, 16, 17, 18, 19]}
+WA_VARIANTS = {np.float64: [17, 18, 19, 20, 21, 22, 23], np.float32: [14, 15, 16, 17, 18, 19, 20, 21]}
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])

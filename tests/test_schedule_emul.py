@@ -156,3 +156,36 @@ def test_wa_guard_handles_what_the_unguarded_step_must_not_see(oracle, emul):
     oracle.iterate(a, D, -99999.0, po.ADD, 3)
     err = run_wa(emul, 0, po.ADD, 0, b, D, -99999.0, 3, 4)
     assert not err.any() and np.array_equal(a, b) and np.array_equal(np.signbit(a), np.signbit(b))
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_wa_staggered_schedule_is_bit_exact(oracle, emul, dt):
+    """kOptStagger: triple slot 1 runs half a step behind slot 0, windows stay in registers across the CTA barrier in
+    between, rows go home half a step after they are finished. Same ring (no extra rows): the emulator's hazard and
+    same-half-step race counters must stay at zero."""
+    rng = np.random.default_rng(77)
+    W_, TWV = C.c_int(), C.c_int()
+    for cfg in (1, 4):
+        emul.wa_emul_cfg_info(cfg, C.byref(W_), C.byref(TWV))
+        for rows, cols, chunk_triples in ((40, 70, 0), (31, TWV.value + 40, 4), (25, 2 * TWV.value + 7, 3), (1, 1, 0), (3, 200, 1), (64, 90, 7)):
+            for mod, mode in ((po.ADD, 4), (po.ADD, 5), (po.SUBTRACT, 4)):
+                D, Wt = random_case(rng, rows, cols, dt)
+                a, b = Wt.copy(), Wt.copy()
+                oracle.iterate(a, D, -99999.0, mod, 3)
+                err = run_wa(emul, cfg, mod, mode, b, D, -99999.0, 3, chunk_triples)
+                assert not err.any(), (cfg, rows, cols, mod, err)
+                assert np.array_equal(a, b), (cfg, rows, cols, mod, mode, int((a != b).sum()))
+    # unguarded on a clean grid
+    D, Wt = random_case(rng, 33, 420, dt, wet_fraction=0.5, nodata_fraction=0.15)
+    a, b = Wt.copy(), Wt.copy()
+    oracle.iterate(a, D, -99999.0, po.ADD, 4)
+    err = run_wa(emul, 1, po.ADD, 7, b, D, -99999.0, 4, 0)
+    assert not err.any() and np.array_equal(a, b)
+
+
+def test_wa_staggered_hazard_checks_fire_when_ring_is_too_small():
+    lib = _build(extra=("-DWDPM_NRING_DELTA=-3",), name="libmw_emul_shrunk.so")
+    rng = np.random.default_rng(5)
+    D, Wt = random_case(rng, 50, 400, np.float64)
+    err = run_wa(lib, 1, po.ADD, 4, Wt.copy(), D, -99999.0, 1, 0)
+    assert err[0] > 0 or err[1] > 0

@@ -271,19 +271,34 @@ struct DrainEvent {
     int pad;
 };
 
+// Event buffers rotate over kEventSlots launches: launch L records into buffer L % 3 and folds buffer (L-1) % 3.
+// Three, not two, because of row stripes: a contact is recorded in the buffer of the stripe that OWNS THE OUTLET
+// (over NVLink when the centre lies in the neighbouring stripe - an outlet within one row of a stripe border is
+// drained by centres of both stripes), so that one accumulator sees all contacts of an outlet in sub-pass order and
+// its total does not depend on the partition. The neighbour's launch L+1 may start (and record) while this
+// stripe's launch L+1 is still folding buffer L % 3; launch L+2 of the neighbour, which reuses buffer (L-1) % 3,
+// cannot start before this stripe's launch L+1 has finished (halo flags), i.e. after that buffer was folded.
+constexpr int kEventSlots = 3;
+__host__ __device__ __forceinline__ int next_event_slot(int s) { return s == kEventSlots - 1 ? 0 : s + 1; }
+__host__ __device__ __forceinline__ int prev_event_slot(int s) { return s == 0 ? kEventSlots - 1 : s - 1; }
+
 template <typename T>
 struct DrainState {
     T* totaldrain;          // [n_outlets] device accumulators
-    DrainEvent<T>* events;  // [2][n_outlets][9*kMaxItersPerLaunch], double-buffered by launch parity
+    DrainEvent<T>* events;  // [kEventSlots][n_outlets][9*kMaxItersPerLaunch]
     const int* outlet_rc;   // [n_outlets][2] padded (row, col) of each outlet in this solver's rows
     int n_outlets;
+    // row stripes: the event buffers of the stripes above / below (peer memory; nullptr = none) and this stripe's owned rows
+    DrainEvent<T>* events_up;
+    DrainEvent<T>* events_dn;
+    int P;
 };
 
 constexpr int kEventsPerBuffer = 9 * kMaxItersPerLaunch;
 
 template <typename T>
-__device__ __forceinline__ DrainEvent<T>* event_slot(const DrainState<T>& ds, int parity, int outlet, int slot) {
-    return ds.events + ((size_t)parity * ds.n_outlets + outlet) * kEventsPerBuffer + slot;
+__device__ __forceinline__ DrainEvent<T>* event_slot(DrainEvent<T>* events, int n_outlets, int buffer, int outlet, int slot) {
+    return events + ((size_t)buffer * n_outlets + outlet) * kEventsPerBuffer + slot;
 }
 
 // index of the outlet at padded (row, col); -1 if none (cannot happen for a marked cell)
@@ -296,9 +311,9 @@ __device__ __forceinline__ int outlet_index(const DrainState<T>& ds, int row, in
 
 // Fold one event buffer: thread t of the calling group takes outlets t, t + nthreads, ...
 template <typename T>
-__device__ __forceinline__ void fold_events(const DrainState<T>& ds, int parity, int t, int nthreads) {
+__device__ __forceinline__ void fold_events(const DrainState<T>& ds, int buffer, int t, int nthreads) {
     for (int k = t; k < ds.n_outlets; k += nthreads) {
-        DrainEvent<T>* ev = event_slot(ds, parity, k, 0);
+        DrainEvent<T>* ev = event_slot(ds.events, ds.n_outlets, buffer, k, 0);
         T td = ds.totaldrain[k];
         bool any = false;
         for (int e = 0; e < kEventsPerBuffer; e++) {
@@ -314,8 +329,8 @@ __device__ __forceinline__ void fold_events(const DrainState<T>& ds, int parity,
 }
 
 template <typename T>
-__global__ void k_fold_events(DrainState<T> ds, int parity) {
-    if (blockIdx.x == 0) fold_events(ds, parity, (int)threadIdx.x, (int)blockDim.x);
+__global__ void k_fold_events(DrainState<T> ds, int buffer) {
+    if (blockIdx.x == 0) fold_events(ds, buffer, (int)threadIdx.x, (int)blockDim.x);
 }
 
 // Mark / unmark outlet cells in the elevation grid (relax.cuh, outlet_mark). `saved` keeps the
@@ -336,14 +351,15 @@ __global__ void k_mark_outlets(T* __restrict__ d, Geom g, const int* __restrict_
 // reports the events (halo copies recompute the same contacts). `slot`: sub-pass slot in the buffer.
 template <typename T>
 __device__ __noinline__ void drain_tile_near_outlets(T* w0, T* w1, T* w2, const T* d0, const T* d1, const T* d2, int j,
-                                                     int mask, DrainState<T> ds, int parity, int slot, int crow, int ccol,
+                                                     int mask, DrainState<T> ds, int buffer, int slot, int crow, int ccol,
                                                      bool owner, bool direct) {
     T evo[8], evc[8];
     int pos[8];
     const int n = relax_tile_near_outlets<T>(w0, w1, w2, d0, d1, d2, j, mask, evo, evc, pos);
     if (!owner) return;
     for (int i = 0; i < n; i++) {
-        const int k = outlet_index(ds, crow + pos[i] / 3 - 1, ccol + pos[i] % 3 - 1);
+        const int orow = crow + pos[i] / 3 - 1;
+        const int k = outlet_index(ds, orow, ccol + pos[i] % 3 - 1);
         if (k < 0) continue;
         if (direct) {  // colour kernel: one launch per sub-pass, a single writer per outlet
             T td = ds.totaldrain[k];
@@ -351,7 +367,11 @@ __device__ __noinline__ void drain_tile_near_outlets(T* w0, T* w1, T* w2, const 
             td = td + evc[i];
             ds.totaldrain[k] = td;
         } else {
-            DrainEvent<T>* ev = event_slot(ds, parity, k, slot);
+            // the stripe that owns the outlet's row keeps its total
+            DrainEvent<T>* base = ds.events;
+            if (ds.events_up && orow < 0) base = ds.events_up;
+            else if (ds.events_dn && orow >= ds.P) base = ds.events_dn;
+            DrainEvent<T>* ev = event_slot(base, ds.n_outlets, buffer, k, slot);
             ev->w_outlet = evo[i];
             ev->w_centre = evc[i];
             ev->valid = 1;
@@ -492,7 +512,7 @@ struct FusedParams {
     int n_strips;
     int chunk_triples;  // owned row triples per CTA
     int total_triples;  // ceil((R+2)/3)
-    int launch_parity;  // drain event buffer written by this launch
+    int launch_slot;    // drain event buffer written by this launch (0 .. kEventSlots-1)
     DrainState<T> ds;
     // Row stripes: the halo exchange is part of this kernel. Rows the neighbouring stripes read
     // (my first kHaloBelow owned rows for the stripe above, my last kHaloAbove for the stripe below)
@@ -592,12 +612,13 @@ __device__ __forceinline__ void issue_row_loads(const FusedParams<T>& p, const M
     }
 }
 
-// rows finished by the last phase in step s: C-type rows 3m+2 .. 3m+4
+// rows finished by the last phase in step s: C-type rows 3m+2 .. 3m+4 (only_t >= 0: of that triple slot only)
 template <typename CFG, typename T>
-__device__ __forceinline__ void issue_row_stores(const FusedParams<T>& p, const MwTile<CFG>& tile, T* ring_w, int s) {
+__device__ __forceinline__ void issue_row_stores(const FusedParams<T>& p, const MwTile<CFG>& tile, T* ring_w, int s, int only_t = -1) {
     const size_t col0 = (size_t)(tile.x0 + kPadLeft);
     bool any = false;
     for (int t = 0; t < CFG::NT; t++) {
+        if (only_t >= 0 && t != only_t) continue;
         const int m = tile.triple(s, CFG::NPH - 1, t);
         for (int k = 0; k < 3; k++) {
             const int row = 3 * m + 2 + k;
@@ -613,6 +634,37 @@ __device__ __forceinline__ void issue_row_stores(const FusedParams<T>& p, const 
         }
     }
     if (any) bulk_commit();
+}
+
+// End of a stripe's iteration kernel: say that my rows have landed in the neighbours' memory and that I have read
+// my halo rows (see FusedParams); the last CTA to say so raises the neighbour's arrival flag.
+template <typename CFG, typename T>
+__device__ __forceinline__ void halo_handshake(const FusedParams<T>& p, const MwTile<CFG>& tile) {
+    const bool exp_up = p.up_flags && 3 * tile.m0 < kHaloBelow;
+    // downwards the flag also licenses the stripe below to overwrite MY bottom-halo rows [P, P+kHaloBelow) in the
+    // buffer this iteration reads, so every CTA that STAGES one of those rows counts (3*(m1+BOT_TRIPLES) > P), not
+    // only those that own the exported rows; such a CTA may export nothing and only bumps the counter.
+#ifdef WDPM_TEST_HOOKS
+    const int dn_reach = p.dbg_old_dn_count ? kHaloAbove : kHaloBelow;
+#else
+    constexpr int dn_reach = kHaloBelow;
+#endif
+    const bool exp_dn = p.dn_flags && 3 * tile.m1 > p.P_self - dn_reach && 3 * tile.m0 < p.P_self;
+    if (exp_up || exp_dn) {
+        // my rows have landed, also in the neighbour's memory; the CTA that is last to say so raises the flag
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __threadfence_system();
+        if (exp_up && atomicAdd(&p.self_flags->push_count, 1) == p.up_ctas - 1) {
+            p.self_flags->push_count = 0;
+            __threadfence_system();
+            st_release_sys(&p.up_flags->from_below, p.epoch);
+        }
+        if (exp_dn && atomicAdd(&p.self_flags->push_count_dn, 1) == p.dn_ctas - 1) {
+            p.self_flags->push_count_dn = 0;
+            __threadfence_system();
+            st_release_sys(&p.dn_flags->from_above, p.epoch);
+        }
+    }
 }
 
 // NBAR = CTA-wide barriers per step the compute threads execute (this warp takes part in each)
@@ -634,13 +686,13 @@ __device__ __forceinline__ void data_movement_warp(const FusedParams<T>& p, cons
     for (int s = 0; s < tile.n_steps; s++) {
         WDPM_TL(0);
         if (lead) {
-            if (s > 0) {
-                issue_row_stores<CFG, T>(p, tile, ring_w, s - 1);
-                // ring slots reused by the next prefetch must have been read out by their stores:
-                // only the group committed just now may still be in flight
-                bulk_wait_read<1>();
-            }
+            // The prefetch goes out first: phase 0 of step s + PF waits for it, and at PF = 1 a step is barely longer
+            // than the trip to HBM. The ring slots it overwrites belonged to rows written home by the store group
+            // of step s - 2 (committed a whole step ago), which must have been read out: every group committed so
+            // far. The rows of step s - 1, stored just below, lie elsewhere in the ring (mw_schedule.h, NRING_MIN).
+            if (s > 1) bulk_wait_read<0>();
             if (s + PF < tile.n_steps) issue_row_loads<CFG, T>(p, tile, ring_w, ring_d, bars, s + PF);
+            if (s > 0) issue_row_stores<CFG, T>(p, tile, ring_w, s - 1);
         }
         __syncwarp();
         WDPM_TL(1);
@@ -651,31 +703,44 @@ __device__ __forceinline__ void data_movement_warp(const FusedParams<T>& p, cons
     if (lead) {
         issue_row_stores<CFG, T>(p, tile, ring_w, tile.n_steps - 1);
         bulk_wait_read<0>();
-        const bool exp_up = p.up_flags && 3 * tile.m0 < kHaloBelow;
-        // downwards the flag also licenses the stripe below to overwrite MY bottom-halo rows [P, P+kHaloBelow) in the
-        // buffer this iteration reads, so every CTA that STAGES one of those rows counts (3*(m1+BOT_TRIPLES) > P), not
-        // only those that own the exported rows; such a CTA may export nothing and only bumps the counter.
-#ifdef WDPM_TEST_HOOKS
-        const int dn_reach = p.dbg_old_dn_count ? kHaloAbove : kHaloBelow;
-#else
-        constexpr int dn_reach = kHaloBelow;
-#endif
-        const bool exp_dn = p.dn_flags && 3 * tile.m1 > p.P_self - dn_reach && 3 * tile.m0 < p.P_self;
-        if (exp_up || exp_dn) {
-            // my rows have landed, also in the neighbour's memory; the CTA that is last to say so raises the flag
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-            __threadfence_system();
-            if (exp_up && atomicAdd(&p.self_flags->push_count, 1) == p.up_ctas - 1) {
-                p.self_flags->push_count = 0;
-                __threadfence_system();
-                st_release_sys(&p.up_flags->from_below, p.epoch);
-            }
-            if (exp_dn && atomicAdd(&p.self_flags->push_count_dn, 1) == p.dn_ctas - 1) {
-                p.self_flags->push_count_dn = 0;
-                __threadfence_system();
-                st_release_sys(&p.dn_flags->from_above, p.epoch);
+        halo_handshake<CFG, T>(p, tile);
+    }
+}
+
+// The STAGGERED schedule (k_fused_wa with kOptStagger, NT = 2): the row groups of triple slot 1 run half a step
+// behind those of slot 0, the CTA meets every half step. Half step h: slot-0 groups do the first half of step h/2
+// (h even) or its second half (h odd); slot-1 groups the second half of step (h-2)/2 (h even) or the first half of
+// step (h-1)/2 (h odd). Rows finished by the last phase are written home half a step after they are done, slot 0
+// and slot 1 in bulk groups of their own; loads stay once per step. The ring needs no extra rows: a load for step
+// s+PF lands at most 31 rows ahead of the oldest row still being computed and 34 ahead of the oldest row whose
+// write-back may be in flight (PF = 1; the ring has 36), and the group before that has been waited for.
+template <typename CFG, typename T>
+__device__ __forceinline__ void data_movement_warp_staggered(const FusedParams<T>& p, const MwTile<CFG>& tile, T* ring_w, T* ring_d, uint64_t* bars, bool lead) {
+    static_assert(CFG::NT == 2, "the staggered schedule splits a step by triple slot");
+    constexpr int PF = CFG::PF;
+    const int n = tile.n_steps;
+    if (lead)
+        for (int s = 0; s < PF && s < n; s++) issue_row_loads<CFG, T>(p, tile, ring_w, ring_d, bars, s);
+    for (int h = 0; h <= 2 * n; h++) {
+        if (lead) {
+            const int s = h >> 1;
+            if ((h & 1) == 0) {
+                if (s > 0) {
+                    issue_row_stores<CFG, T>(p, tile, ring_w, s - 1, 0);
+                    bulk_wait_read<1>();
+                }
+                if (s + PF < n) issue_row_loads<CFG, T>(p, tile, ring_w, ring_d, bars, s + PF);
+            } else if (s > 0) {
+                issue_row_stores<CFG, T>(p, tile, ring_w, s - 1, 1);
             }
         }
+        __syncwarp();
+        __syncthreads();
+    }
+    if (lead) {
+        issue_row_stores<CFG, T>(p, tile, ring_w, n - 1, 1);
+        bulk_wait_read<0>();
+        halo_handshake<CFG, T>(p, tile);
     }
 }
 
@@ -702,7 +767,7 @@ k_fused(const FusedParams<T> p) {
     MwTile<CFG> tile;
     tile.init(strip, chunk, p.chunk_triples, p.total_triples);
 
-    if (MODULE == kDrain && blockIdx.x == 0) fold_events(p.ds, p.launch_parity ^ 1, tid, NALL);
+    if (MODULE == kDrain && blockIdx.x == 0) fold_events(p.ds, prev_event_slot(p.launch_slot), tid, NALL);
 
     // Drain: does any outlet lie in the rows and columns this CTA stages? (If not, no tile of this CTA
     // can see an outlet mark and the per-tile test is skipped.)
@@ -831,7 +896,7 @@ k_fused(const FusedParams<T> p) {
                     T* w0 = wrow[k][0]; T* w1 = wrow[k][1]; T* w2 = wrow[k][2];
                     const int mask = outlet_mask_3x3<T>(w0 + DOFF, w1 + DOFF, w2 + DOFF, j);
                     if (mask) {
-                        drain_tile_near_outlets<T>(w0, w1, w2, w0 + DOFF, w1 + DOFF, w2 + DOFF, j, mask, p.ds, p.launch_parity,
+                        drain_tile_near_outlets<T>(w0, w1, w2, w0 + DOFF, w1 + DOFF, w2 + DOFF, j, mask, p.ds, p.launch_slot,
                                                    (it_ph[k] / 3) * 9 + it_q[k] * 3 + COFS, crow, ccol,
                                                    tile.owns_row(crow) && tile.owns_col(ccol), false);
                     } else {
@@ -900,6 +965,10 @@ k_fused(const FusedParams<T> p) {
 // ---------------------------------------------------------------------------
 
 constexpr int kOptNoGuard = 8;
+// OPT bit 4: STAGGERED schedule - the row groups of triple slot 1 run half a step behind those of slot 0 (see
+// data_movement_warp_staggered), so that one half of the warps loads / stores its windows while the other half is in
+// the middle of its chains: the shared-memory bursts that open and close a step no longer meet an idle issue port.
+constexpr int kOptStagger = 16;
 
 template <typename CFG, typename T>
 constexpr size_t wa_smem_bytes() {
@@ -932,6 +1001,8 @@ k_fused_wa(const FusedParams<T> p) {
     constexpr int W = CFG::W, NT = CFG::NT, NPH = CFG::NPH, NRING = CFG::NRING, NSTAGE = CFG::NSTAGE, KW = CFG::KW;
     constexpr bool FAST = (OPT & kOptAddFast) && MODULE == kAdd;  // fp64: push_add_fast, fp32: push_add_nocap
     constexpr bool GUARD = !(FAST && (OPT & kOptNoGuard));
+    constexpr bool STAGGER = (OPT & kOptStagger) != 0;
+    static_assert(!STAGGER || CFG::NT == 2, "the staggered schedule splits a step by triple slot");
     using V2 = typename Vec2<T>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* ring_w = reinterpret_cast<T*>(smem_raw);
@@ -957,32 +1028,42 @@ k_fused_wa(const FusedParams<T> p) {
             asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
             if (tid >= NTHREADS + 32) return;
         }
-        data_movement_warp<CFG, T, 1>(p, tile, ring_w, ring_d, bars, tid == NTHREADS);
+        if constexpr (STAGGER) data_movement_warp_staggered<CFG, T>(p, tile, ring_w, ring_d, bars, tid == NTHREADS);
+        else data_movement_warp<CFG, T, 1>(p, tile, ring_w, ring_d, bars, tid == NTHREADS);
         return;
     }
     if (REALLOC) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kComputeRegs));
 
-    // this warp: phase ph (= colour row offset, K = 1), triple slot t, column block kw of the row triple
+    // this warp: phase ph (= colour row offset, K = 1), triple slot t, column block kw of the row triple. With the
+    // staggered schedule the slots alternate over the warps of a phase (and the other way round in the next phase),
+    // so every scheduler hosts warps of both halves of the step.
     const int warp = tid >> 5, lane = tid & 31;
-    const int kw = warp % KW, grp = warp / KW, t = grp % NT, ph = grp / NT;
+    const int wph = warp % (NT * KW), ph = warp / (NT * KW);
+    const int t = STAGGER ? ((wph & 1) ^ (ph & 1)) : wph / KW;
+    const int kw = STAGGER ? wph / NT : wph % KW;
+    const int grp = ph * NT + t;
     const int cb = CFG::WSTRIDE * kw + CFG::CPL * lane;  // window column of the lane's column 0
     const bool stores = lane < 31;
     constexpr int DOFF = NRING * W;
     uint64_t* gbar = &group_bars[grp];
 
-    for (int s = 0; s < tile.n_steps; s++) {
+    T wt[3][8], dd[3][8];
+    T* wrow[3] = {ring_w, ring_w, ring_w};
+    bool run = false;
+
+    // first part of step s: window into registers, first colour sub-pass (and, staggered, half of the second)
+    auto begin_step = [&](int s) {
         const int m = tile.m_lo + NT * s - ph * CFG::LAG + t;
-        const bool run = tile.runnable(m, ph);
+        run = tile.runnable(m, ph);
         WDPM_TL(0);
-        if (ph == 0 && step_has_loads<CFG>(tile, s)) mbar_wait(&bars[s % NSTAGE], (uint32_t)((s / NSTAGE) & 1));
+        if (ph == 0 && tile.staged(m)) mbar_wait(&bars[s % NSTAGE], (uint32_t)((s / NSTAGE) & 1));
         WDPM_TL(1);
         if (run) {
             const int row0 = 3 * m + ph;
             int s0 = tile.ring_slot(row0);
             int s1 = s0 + 1; if (s1 == NRING) s1 = 0;
             int s2 = s1 + 1; if (s2 == NRING) s2 = 0;
-            T* wrow[3] = {ring_w + s0 * W + cb, ring_w + s1 * W + cb, ring_w + s2 * W + cb};
-            T wt[3][8], dd[3][8];
+            wrow[0] = ring_w + s0 * W + cb; wrow[1] = ring_w + s1 * W + cb; wrow[2] = ring_w + s2 * W + cb;
 #pragma unroll
             for (int r = 0; r < 3; r++) {
 #pragma unroll
@@ -998,12 +1079,22 @@ k_fused_wa(const FusedParams<T> p) {
             }
             wa_relax_pair<T, MODULE, 0, FAST, GUARD>(wt, dd);
             WDPM_TL(2);
-            // every lane's window is in registers (the relax above consumed it): tell the row group
-            __syncwarp();
-            if (lane == 0) mbar_arrive(gbar);
+        }
+        // every lane's window is in registers (the relax above consumed it): tell the row group. A group that
+        // does not run this step arrives too, which keeps the barrier's phase in step with s.
+        __syncwarp();
+        if (lane == 0) mbar_arrive(gbar);
+        if (run) {
 #pragma unroll
             for (int r = 0; r < 3; r++) wt[r][6] = shfl_from_right(wt[r][0]);
-            wa_relax_pair<T, MODULE, 1, FAST, GUARD>(wt, dd);
+            if (STAGGER) wa_relax_pair<T, MODULE, 1, FAST, GUARD, 1>(wt, dd);
+        }
+    };
+    // the rest of step s, and the write-back
+    auto end_step = [&](int s) {
+        if (run) {
+            if (STAGGER) wa_relax_pair<T, MODULE, 1, FAST, GUARD, 2>(wt, dd);
+            else wa_relax_pair<T, MODULE, 1, FAST, GUARD>(wt, dd);
             WDPM_TL(3);
 #pragma unroll
             for (int r = 0; r < 3; r++) wt[r][7] = shfl_from_right(wt[r][1]);
@@ -1022,14 +1113,30 @@ k_fused_wa(const FusedParams<T> p) {
                     }
                 }
             }
-        } else {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(gbar);  // keep the group barrier's phase in step with s
         }
-        fence_proxy_async();  // make this step's smem writes visible to the bulk-store engine
-        WDPM_TL(7);
-        __syncthreads();
-        WDPM_TL(8);
+    };
+
+    if (!STAGGER) {
+        for (int s = 0; s < tile.n_steps; s++) {
+            begin_step(s);
+            end_step(s);
+            fence_proxy_async();  // make this step's smem writes visible to the bulk-store engine
+            WDPM_TL(7);
+            __syncthreads();
+            WDPM_TL(8);
+        }
+    } else {
+        // half step h: slot-0 groups begin step h/2 (h even) or end it (h odd); slot-1 groups half a step later
+        for (int h = 0; h <= 2 * tile.n_steps; h++) {
+            const int s = (h - t) >> 1;  // the step this warp is in (h - t >= 0 wherever it is used)
+            if (((h - t) & 1) == 0) {
+                if (h >= t && s < tile.n_steps) begin_step(s);
+            } else {
+                if (h > t && s < tile.n_steps) end_step(s);
+            }
+            fence_proxy_async();
+            __syncthreads();
+        }
     }
 }
 
@@ -1057,7 +1164,7 @@ struct ResidentParams {
     int TR, TC;     // owned rows / cols per CTA (multiples of 3)
     int n_tx;       // CTAs per grid row
     int n_iters;
-    int launch_parity;  // drain event buffer of the first iteration
+    int launch_slot;    // drain event buffer of the first iteration
     DrainState<T> ds;
 };
 
@@ -1081,11 +1188,11 @@ k_resident(const ResidentParams<T> p) {
         const int i = k / SC, j = k - i * SC;
         sd[k] = p.dem[base + (size_t)i * pitch + j];
     }
-    int cur = p.cur, parity = p.launch_parity;
+    int cur = p.cur, evbuf = p.launch_slot;
     for (int it = 0; it < p.n_iters; it++) {
         const T* __restrict__ win = p.w[cur];
         T* __restrict__ wout = p.w[cur ^ 1];
-        if (MODULE == kDrain && blockIdx.x == 0) fold_events(p.ds, parity ^ 1, tid, NTHREADS);
+        if (MODULE == kDrain && blockIdx.x == 0) fold_events(p.ds, prev_event_slot(evbuf), tid, NTHREADS);
         for (int k = tid; k < SR * SC; k += NTHREADS) {
             const int i = k / SC, j = k - i * SC;
             sw[k] = win[base + (size_t)i * pitch + j];
@@ -1105,7 +1212,7 @@ k_resident(const ResidentParams<T> p) {
                     if (mask) {
                         const int crow = r0 + i + 1, ccol = c0 + j;
                         // only the CTA that owns the centre reports the contact (halo copies recompute it)
-                        drain_tile_near_outlets<T>(w0, w1, w2, d0, d1, d2, j, mask, p.ds, parity, sub, crow, ccol,
+                        drain_tile_near_outlets<T>(w0, w1, w2, d0, d1, d2, j, mask, p.ds, evbuf, sub, crow, ccol,
                                                    crow >= r_own && crow < r_own + p.TR && ccol >= c_own && ccol < c_own + p.TC, false);
                         continue;
                     }
@@ -1121,9 +1228,9 @@ k_resident(const ResidentParams<T> p) {
         }
         grid.sync();
         cur ^= 1;
-        parity ^= 1;
+        evbuf = next_event_slot(evbuf);
     }
-    if (MODULE == kDrain && blockIdx.x == 0) fold_events(p.ds, parity ^ 1, tid, NTHREADS);
+    if (MODULE == kDrain && blockIdx.x == 0) fold_events(p.ds, prev_event_slot(evbuf), tid, NTHREADS);
 }
 
 }  // namespace wdpm

@@ -293,7 +293,11 @@ WDPM_HD void push_sel(T dc, T& wc, T dn, T& wn) {
 // has wc = +0, and with wc = +0 every step moves +0 or nothing: an open gate h > 0 means dc = sc > sn, so x = wc = 0;
 // an invalid centre (dc = S) likewise has x = wc = 0. Adding +0 to water that is never -0.0 changes nothing.
 // Add only, with the cap-free steps (solver.cu decides when).
-template <typename T, int MODULE, int C, bool FAST, bool GUARD>
+// PART: 0 = all eight neighbour steps; 1 = the first four, 2 = the last four (the staggered schedule cuts the
+// middle sub-pass of a step in two, kernels.cuh). Between the halves the centre's running water lives in the
+// window like any other cell, and the second half decides again whether the centre is active: a centre that ran
+// dry in the first half has wc = +0, with which the remaining steps move nothing in the reference either.
+template <typename T, int MODULE, int C, bool FAST, bool GUARD, int PART = 0>
 WDPM_HD void wa_relax_pair(T (&w)[3][8], const T (&d)[3][8]) {
     T dcA = d[1][C + 1], dcB = d[1][C + 4];
     T wcA = w[1][C + 1], wcB = w[1][C + 4];
@@ -312,9 +316,14 @@ WDPM_HD void wa_relax_pair(T (&w)[3][8], const T (&d)[3][8]) {
         push_sel<T, MODULE, FAST>(dcA, wcA, d[r][C + c], w[r][C + c]);          \
         push_sel<T, MODULE, FAST>(dcB, wcB, d[r][C + 3 + c], w[r][C + 3 + c]);  \
     } while (0)
-    WDPM_PUSH2(0, 0); WDPM_PUSH2(0, 1); WDPM_PUSH2(0, 2);
-    WDPM_PUSH2(1, 0); WDPM_PUSH2(1, 2);
-    WDPM_PUSH2(2, 0); WDPM_PUSH2(2, 1); WDPM_PUSH2(2, 2);
+    if (PART != 2) {
+        WDPM_PUSH2(0, 0); WDPM_PUSH2(0, 1); WDPM_PUSH2(0, 2);
+        WDPM_PUSH2(1, 0);
+    }
+    if (PART != 1) {
+        WDPM_PUSH2(1, 2);
+        WDPM_PUSH2(2, 0); WDPM_PUSH2(2, 1); WDPM_PUSH2(2, 2);
+    }
 #undef WDPM_PUSH2
     w[1][C + 1] = (!GUARD || actA) ? wcA : keepA;
     w[1][C + 4] = (!GUARD || actB) ? wcB : keepB;

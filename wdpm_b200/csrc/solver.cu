@@ -157,6 +157,8 @@ const std::vector<FusedVariant<double>>& fused_variants<double>() {
         make_wa_variant<double, WaCfg<2, 2, 1>, kOptAddFast>(),                             // 19: as 17 without register reallocation
         make_wa_variant<double, WaCfg<2, 1, 1>, kOptAddFast>(),                             // 20: one triple per phase (6 warps; small grids)
         make_wa_variant<double, WaCfg<3, 1, 1>, kOptAddFast>(),                             // 21: 566-column window, one triple per phase (9 warps)
+        make_wa_variant<double, WaCfg<2, 2, 1>, kOptAddFast | kOptRegRealloc | kOptStagger>(),  // 22: as 17, staggered: triple slot 1 half a step behind slot 0
+        make_wa_variant<double, WaCfg<1, 2, 1>, kOptAddFast | kOptStagger>(),               // 23: test window for 22
     };
     return v;
 }
@@ -182,6 +184,8 @@ const std::vector<FusedVariant<float>>& fused_variants<float>() {
         make_wa_variant<float, WaCfg<2, 2, 1>, kOptAddFast, 2>(),  // 17: as 14, two CTAs per SM
         make_wa_variant<float, WaCfg<3, 2, 1>, kOptAddFast>(),     // 18: 566-column window, 18 warps
         make_wa_variant<float, WaCfg<4, 2, 1>, kOptRegRealloc>(),  // 19: as 16 with the reference form of the step (comparison)
+        make_wa_variant<float, WaCfg<4, 2, 1>, kOptAddFast | kOptRegRealloc | kOptStagger>(),  // 20: as 16, staggered
+        make_wa_variant<float, WaCfg<1, 2, 1>, kOptAddFast | kOptStagger>(),               // 21: test window for 20
     };
     return v;
 }
@@ -226,7 +230,7 @@ struct wdpm_solver {
     int n_outlets = 0;
     bool marks_applied = false;
     bool have_outlet = false;
-    int launch_parity = 0;
+    int launch_slot = 0;       // drain event buffer of the next launch (kernels.cuh, kEventSlots)
 
     BlockPartial* partials = nullptr;
     BlockPartial* d_result = nullptr;
@@ -243,6 +247,7 @@ struct wdpm_solver {
         bool present = false;
         void* w[2] = {nullptr, nullptr};
         HaloFlags* flags = nullptr;
+        void* events = nullptr;  // the neighbour's drain event buffers (same allocation as its flags)
         int P = 0;
         bool ipc = false;
     } above, below;
@@ -271,10 +276,15 @@ DrainState<T> drain_state(wdpm_solver* s) {
     ds.events = static_cast<DrainEvent<T>*>(s->events);
     ds.outlet_rc = s->d_outlet_rc;
     ds.n_outlets = s->n_outlets;
+    // row stripes: contacts with an outlet in a neighbour's rows are recorded in that neighbour's buffer (kernels.cuh)
+    ds.events_up = (s->stripe && s->above.present) ? static_cast<DrainEvent<T>*>(s->above.events) : nullptr;
+    ds.events_dn = (s->stripe && s->below.present) ? static_cast<DrainEvent<T>*>(s->below.events) : nullptr;
+    ds.P = s->P;
     return ds;
 }
 
 constexpr int kMaxOutlets = WDPM_MAX_OUTLETS;
+constexpr size_t kFlagsBytes = 256;  // HaloFlags, padded; the drain event buffers follow in the same allocation
 
 int grid_for(long long n, int threads, int sm_count) {
     long long b = (n + threads - 1) / threads;
@@ -364,7 +374,7 @@ int fused_iterations(wdpm_solver* s, int n) {
         p.n_strips = s->n_strips;
         p.chunk_triples = s->chunk_triples;
         p.total_triples = s->total_triples;
-        p.launch_parity = s->launch_parity;
+        p.launch_slot = s->launch_slot;
         p.ds = drain_state<T>(s);
         if (s->stripe && s->epoch > 0 && (s->above.present || s->below.present)) {
             k_halo_wait<<<1, 32, 0, s->stream>>>(s->flags, s->above.present, s->below.present, s->epoch, s->halo_timeout_ns);
@@ -374,10 +384,15 @@ int fused_iterations(wdpm_solver* s, int n) {
         CUDA_TRY(pick_launch<T>(s, v)(p, s->n_strips * s->n_chunks, s->stream));
         s->launches++;
         s->cur ^= 1;
-        s->launch_parity ^= 1;
+        s->launch_slot = next_event_slot(s->launch_slot);
     }
     if (s->module == WDPM_DRAIN && n_launch > 0) {
-        k_fold_events<T><<<1, 256, 0, s->stream>>>(drain_state<T>(s), s->launch_parity ^ 1);
+        if (s->stripe && (s->above.present || s->below.present)) {
+            // the neighbours' last iteration records contacts with my outlets in my buffers: wait for it
+            k_halo_wait<<<1, 32, 0, s->stream>>>(s->flags, s->above.present, s->below.present, s->epoch, s->halo_timeout_ns);
+            s->launches++;
+        }
+        k_fold_events<T><<<1, 256, 0, s->stream>>>(drain_state<T>(s), prev_event_slot(s->launch_slot));
         s->launches++;
         CUDA_TRY(cudaGetLastError());
     }
@@ -398,18 +413,24 @@ int fused_launch_only(wdpm_solver* s) {
     p.n_strips = s->n_strips;
     p.chunk_triples = s->chunk_triples;
     p.total_triples = s->total_triples;
-    p.launch_parity = s->launch_parity;
+    p.launch_slot = s->launch_slot;
     p.ds = drain_state<T>(s);
     set_halo_export<T>(s, p);
     CUDA_TRY(pick_launch<T>(s, v)(p, s->n_strips * s->n_chunks, s->stream));
     s->launches++;
     s->cur ^= 1;
-    s->launch_parity ^= 1;
-    if (s->module == WDPM_DRAIN) {
-        k_fold_events<T><<<1, 256, 0, s->stream>>>(drain_state<T>(s), s->launch_parity ^ 1);
-        s->launches++;
-        CUDA_TRY(cudaGetLastError());
-    }
+    s->launch_slot = next_event_slot(s->launch_slot);
+    return WDPM_OK;  // Drain: the contacts are folded by the next launch, or by phase 1 (fold_last_launch)
+}
+
+// Lockstep hosts: fold the contacts of the last iteration once EVERY stripe has run it (a neighbour records the
+// contacts of its centres with my outlets in my buffers).
+template <typename T>
+int fold_last_launch(wdpm_solver* s) {
+    if (s->module != WDPM_DRAIN) return WDPM_OK;
+    k_fold_events<T><<<1, 256, 0, s->stream>>>(drain_state<T>(s), prev_event_slot(s->launch_slot));
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
     return WDPM_OK;
 }
 
@@ -427,7 +448,7 @@ cudaError_t launch_resident(wdpm_solver* s, int n) {
     p.TC = s->res_TC;
     p.n_tx = s->res_ntx;
     p.n_iters = n;
-    p.launch_parity = s->launch_parity;
+    p.launch_slot = s->launch_slot;
     p.ds = drain_state<T>(s);
     void* args[] = {&p};
     auto kern = k_resident<T, MODULE, kResidentThreads>;
@@ -447,7 +468,8 @@ int resident_iterations(wdpm_solver* s, int n) {
     }
     CUDA_TRY(e);
     s->launches++;
-    if (n & 1) { s->cur ^= 1; s->launch_parity ^= 1; }
+    if (n & 1) s->cur ^= 1;
+    s->launch_slot = (s->launch_slot + n) % kEventSlots;
     return WDPM_OK;
 }
 
@@ -803,9 +825,12 @@ int wdpm_create(const wdpm_config* cfg, wdpm_solver** out) {
         s->device_bytes += (long long)grid_bytes;
     }
     s->reduce_blocks = s->sm_count * 8;
-    const size_t ev_bytes = (size_t)2 * kMaxOutlets * kEventsPerBuffer * (s->dtype == WDPM_F64 ? sizeof(DrainEvent<double>) : sizeof(DrainEvent<float>));
-    if ((e = cudaMalloc((void**)&s->flags, sizeof(HaloFlags))) != cudaSuccess) return cleanup(WDPM_E_NOMEM, cudaGetErrorString(e));
-    if ((e = cudaMalloc(&s->totaldrain, 8 * kMaxOutlets)) != cudaSuccess || (e = cudaMalloc(&s->events, ev_bytes)) != cudaSuccess ||
+    // the arrival flags and the drain event buffers share one allocation: both are written by the neighbouring
+    // stripes, and one IPC handle then covers both
+    const size_t ev_bytes = (size_t)kEventSlots * kMaxOutlets * kEventsPerBuffer * (s->dtype == WDPM_F64 ? sizeof(DrainEvent<double>) : sizeof(DrainEvent<float>));
+    if ((e = cudaMalloc((void**)&s->flags, kFlagsBytes + ev_bytes)) != cudaSuccess) return cleanup(WDPM_E_NOMEM, cudaGetErrorString(e));
+    s->events = reinterpret_cast<char*>(s->flags) + kFlagsBytes;
+    if ((e = cudaMalloc(&s->totaldrain, 8 * kMaxOutlets)) != cudaSuccess ||
         (e = cudaMalloc(&s->saved_elev, 8 * kMaxOutlets)) != cudaSuccess ||
         (e = cudaMalloc((void**)&s->d_outlet_rc, sizeof(int) * 2 * kMaxOutlets)) != cudaSuccess ||
         (e = cudaMalloc((void**)&s->partials, sizeof(BlockPartial) * s->reduce_blocks)) != cudaSuccess ||
@@ -847,7 +872,7 @@ int wdpm_destroy(wdpm_solver* s) {
             cudaIpcCloseMemHandle(peer->flags);
         }
     if (s->flags) cudaFree(s->flags);
-    void* ptrs[] = {s->dem, s->w[0], s->w[1], s->oldw, s->totaldrain, s->events, s->saved_elev, s->d_outlet_rc, s->partials, s->d_result, s->outlet_partials, s->d_outlet, s->d_dirty};
+    void* ptrs[] = {s->dem, s->w[0], s->w[1], s->oldw, s->totaldrain, s->saved_elev, s->d_outlet_rc, s->partials, s->d_result, s->outlet_partials, s->d_outlet, s->d_dirty};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->h_result) cudaFreeHost(s->h_result);
@@ -1015,7 +1040,7 @@ int wdpm_set_outlets(wdpm_solver* s, int32_t n, const int32_t* rows, const int32
     s->n_outlets = n;
     s->have_outlet = true;
     CUDA_TRY(cudaMemcpyAsync(s->d_outlet_rc, s->outlet_rc.data(), sizeof(int) * 2 * n, cudaMemcpyHostToDevice, s->stream));
-    CUDA_TRY(cudaMemsetAsync(s->events, 0, (size_t)2 * n * kEventsPerBuffer * (s->dtype == WDPM_F64 ? sizeof(DrainEvent<double>) : sizeof(DrainEvent<float>)), s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->events, 0, (size_t)kEventSlots * n * kEventsPerBuffer * (s->dtype == WDPM_F64 ? sizeof(DrainEvent<double>) : sizeof(DrainEvent<float>)), s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     return s->have_dem ? apply_outlet_marks(s, true) : WDPM_OK;
 }
@@ -1284,6 +1309,8 @@ int wdpm_stripe_upload(wdpm_solver* s, const void* dem_band, const void* water_b
                                    s->stream));
     CUDA_TRY(cudaMemsetAsync(s->flags, 0, sizeof(HaloFlags), s->stream));
     s->epoch = 0;
+    s->launch_slot = 0;  // neighbours must agree on the event buffer rotation as well
+    CUDA_TRY(cudaMemsetAsync(s->events, 0, (size_t)kEventSlots * kMaxOutlets * kEventsPerBuffer * (s->dtype == WDPM_F64 ? sizeof(DrainEvent<double>) : sizeof(DrainEvent<float>)), s->stream));
     s->halo_failed = false;
     *s->h_halo_error = 0;
     s->have_dem = true;
@@ -1333,6 +1360,7 @@ static int connect_side(wdpm_solver* s, wdpm_solver::Peer& peer, const wdpm_stri
         peer.w[0] = o->w[0];
         peer.w[1] = o->w[1];
         peer.flags = o->flags;
+        peer.events = o->events;
         peer.ipc = false;
     } else {
         cudaIpcMemHandle_t h;
@@ -1344,6 +1372,7 @@ static int connect_side(wdpm_solver* s, wdpm_solver::Peer& peer, const wdpm_stri
         void* f = nullptr;
         CUDA_TRY(cudaIpcOpenMemHandle(&f, h, cudaIpcMemLazyEnablePeerAccess));
         peer.flags = static_cast<HaloFlags*>(f);
+        peer.events = static_cast<char*>(f) + kFlagsBytes;
         peer.ipc = true;
     }
     peer.present = true;
@@ -1365,7 +1394,7 @@ int wdpm_stripe_phase(wdpm_solver* s, int32_t phase) {
     if (!s->have_dem) return fail(WDPM_E_STATE, "upload first");
     CUDA_TRY(cudaSetDevice(s->device));
     if (phase == 0) return s->dtype == WDPM_F64 ? fused_launch_only<double>(s) : fused_launch_only<float>(s);
-    if (phase == 1) return WDPM_OK;  // the iteration kernel has already exported the halo rows
+    if (phase == 1) return s->dtype == WDPM_F64 ? fold_last_launch<double>(s) : fold_last_launch<float>(s);
     return fail(WDPM_E_ARG, "phase must be 0 or 1");
 }
 

@@ -142,6 +142,14 @@ class DistributedSolver:
         self.dist.all_gather_object(allr, r)
         return combine_block_results(allr)
 
+    def outlet_drains(self, n: int) -> np.ndarray:
+        """Per-outlet totals of the whole DEM: each is kept by the stripe that owns the outlet's row (0 elsewhere),
+        so the element-wise sum over the stripes is exact."""
+        mine = self.solver.get_outlet_drains(n)
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, mine)
+        return np.sum(parts, axis=0)
+
     def close(self):
         self.dist.barrier()
         self.solver.close()
