@@ -158,6 +158,14 @@ int wdpm_quantize_water(wdpm_solver *s);
 /* water depth at one cell (for totaldrain = max(bigwater[outlet],0), src/WDPMCL.c:1029) */
 int wdpm_get_cell_water(wdpm_solver *s, int32_t row, int32_t col, double *value);
 
+/* The order-free part of the final report (src/WDPMCL.c:1394-1459) computed on the device over the interior cells
+ * this solver owns: cells with dem > nodata (basincount), those of them with water > 0.001 m (watercount, from
+ * which "Final water coverage" and the divisor of "Mean water depth" follow) and the deepest water on a valid cell
+ * ("Max water depth"). Counts add and maxima combine over stripes. The volume sums of the report are NOT here: the
+ * reference accumulates them cell by cell in double and prints them with fixed decimals, which only a sequential
+ * pass over the downloaded grid reproduces digit for digit. Any pointer may be NULL. */
+int wdpm_final_statistics(wdpm_solver *s, int64_t *valid_cells, int64_t *wet_above_1mm, double *max_depth);
+
 /* Order-free 64-bit checksum of the water grid this solver owns (interior cells): sum of
  * bits(w) * (2*index + 1) mod 2^64, index = row-major position in the WHOLE DEM. The sum of the stripes' checksums
  * (mod 2^64) equals the single-solver checksum iff the grids are equal bit for bit, whatever the partition.

@@ -11,7 +11,7 @@
  * The reference's OpenCL path flattens column-major (runoff.cl:33); the layout
  * does not affect any value, only addresses.
  *
- * Parity status: pinned. tests/test_oracle_vs_reference.py checks these
+ * Parity status: pinned. tests/test_oracle.py checks these
  * functions bit-for-bit against the verbatim runoff.cl compiled through
  * oracle/ref_shim (oracle/_ref/librunoffcl_ref.so) and against outputs of the
  * unmodified WDPMCL.c serial backend (oracle/_ref/WDPMCL_ref), and the

@@ -117,6 +117,7 @@ if rank == 0:
                "setup_s": t_setup, "device_bytes_per_gpu": info["device_bytes"], "blocks": lines,
                "water_checksum": f"{checksum:016x}", "outlet_totals_bits": [f"{int(np.float64(v).view(np.uint64)):016x}" for v in per_outlet],
                "outlet_totals_m": [float(v) for v in per_outlet],
+               "total_drain_outlet_order_m": float(np.add.reduce(np.asarray(per_outlet, dtype=np.float64))) if len(per_outlet) < 8 else float(__import__("functools").reduce(lambda x, y: x + y, [float(v) for v in per_outlet])),
                "outlets_on_stripe_borders": [list(o) for o in outlets if any(abs(o[0] - p.row0) <= 1 for p in plan_stripes(n, world)[1:])]}
     print(json.dumps(summary))
     if a.out:

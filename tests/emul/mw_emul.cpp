@@ -235,6 +235,7 @@ void run_cta_wa(const Layout& L, const T* w_in, T* w_out, const T* dem, int stri
 
     for (int s = 0; s < PF && s < tile.n_steps; s++) issue_loads(s);
     for (int s = 0; s < tile.n_steps; s++) {
+        if (CFG::STRICT_ORDER) wait_read(0);  // deep prefetch: the write-backs issued at the end of the step before were read out first
         if (s + PF < tile.n_steps) issue_loads(s + PF);
         for (int grp = 0; grp < NPH * NT; grp++) {
             const int t = grp % NT, ph = grp / NT;
@@ -530,6 +531,8 @@ int dispatch_wa_cfg(int cfg, int module, int mode, T* w, const T* d, int R, int 
         case 2: return dispatch_wa<T, WaCfg<2, 1, 2>>(module, mode, w, d, R, C, nodata, n, ct, e);
         case 3: return dispatch_wa<T, WaCfg<3, 1, 1>>(module, mode, w, d, R, C, nodata, n, ct, e);
         case 4: return dispatch_wa<T, WaCfg<1, 2, 1>>(module, mode, w, d, R, C, nodata, n, ct, e);
+        case 5: return dispatch_wa<T, WaCfg<2, 2, 2, 1>>(module, mode, w, d, R, C, nodata, n, ct, e);
+        case 6: return dispatch_wa<T, WaCfg<1, 1, 2, 1>>(module, mode, w, d, R, C, nodata, n, ct, e);
     }
     return -2;
 }
@@ -588,6 +591,8 @@ int wa_emul_cfg_info(int cfg, int* W, int* TWV) {
         case 2: *W = WaCfg<2, 1, 2>::W; *TWV = WaCfg<2, 1, 2>::TWV; return 0;
         case 3: *W = WaCfg<3, 1, 1>::W; *TWV = WaCfg<3, 1, 1>::TWV; return 0;
         case 4: *W = WaCfg<1, 2, 1>::W; *TWV = WaCfg<1, 2, 1>::TWV; return 0;
+        case 5: *W = WaCfg<2, 2, 2, 1>::W; *TWV = WaCfg<2, 2, 2, 1>::TWV; return 0;
+        case 6: *W = WaCfg<1, 1, 2, 1>::W; *TWV = WaCfg<1, 1, 2, 1>::TWV; return 0;
     }
     return -1;
 }

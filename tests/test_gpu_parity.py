@@ -86,7 +86,7 @@ def _implements(variant, code, mod):
         return False
 
 
-WA_VARIANTS = {np.float64: [17, 18, 19, 20, 21, 22, 23], np.float32: [14, 15, 16, 17, 18, 19, 20, 21]}
+WA_VARIANTS = {np.float64: [17, 18, 19, 20, 21, 22, 23, 24, 25], np.float32: [14, 15, 16, 17, 18, 19, 20, 21, 22, 23]}
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
@@ -523,3 +523,31 @@ def test_tier2_parity_against_the_serial_path(cuda_lib, basin5):
         assert worst <= params.elevation_tol_mm / 1000.0, (name, worst)
         if name == "add":  # serial Add is runoffs == runoffadd bit for bit
             assert np.array_equal(gpu.water, cpu.water)
+
+
+def test_final_statistics_on_the_device(cuda_lib, oracle):
+    """the order-free part of the final report (WDPMCL.c:1394-1459) - valid cells, cells with more than
+    1 mm of water, deepest water - from one device pass; single solver and stripes (counts add, maxima combine)."""
+    from wdpm_b200 import F32, F64, Solver
+    from wdpm_b200.stripes import StripeSolver, connect_in_process, plan_stripes
+    rng = np.random.default_rng(91)
+    for dt, code in ((np.float64, F64), (np.float32, F32)):
+        D, W = random_case(rng, 140, 310, dt, depth=0.004, wet_fraction=0.6)
+        W[3, 5] = dt(7.25)  # the deepest cell, on a valid cell
+        D[3, 5] = dt(500.0)
+        dem, w = D[1:-1, 1:-1], W[1:-1, 1:-1]
+        valid = dem > NODATA
+        want = (int(valid.sum()), int(((w > dt(0.001)) & valid).sum()), float(w[valid].max()))
+        with Solver(140, 310, NODATA, 2, dtype=code) as s:   # Drain: the outlet mark must still count as a valid cell
+            s.upload(dem, w)
+            s.find_outlet()
+            assert s.final_statistics() == want
+        plan = plan_stripes(140, 3)
+        ss = [StripeSolver(140, 310, NODATA, 0, st, dtype=code, fused_variant=2) for st in plan]
+        connect_in_process(ss)
+        for s, st in zip(ss, plan):
+            s.upload_band(dem[st.band_row0:st.band_row0 + st.band_rows], w[st.band_row0:st.band_row0 + st.band_rows])
+        parts = [s.final_statistics() for s in ss]
+        for s in ss:
+            s.close()
+        assert (sum(p[0] for p in parts), sum(p[1] for p in parts), max(p[2] for p in parts)) == want

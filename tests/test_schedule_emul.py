@@ -114,7 +114,7 @@ def run_wa(lib, cfg, module, mode, w, d, nodata, n_launches, chunk_triples):
     return err
 
 
-@pytest.mark.parametrize("cfg", range(4))
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 5, 6])
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
 def test_wa_schedule_is_bit_exact(oracle, emul, cfg, dt):
     """Grids narrower and wider than one strip (several warps per row triple, several strips), chunked rows."""
@@ -188,4 +188,14 @@ def test_wa_staggered_hazard_checks_fire_when_ring_is_too_small():
     rng = np.random.default_rng(5)
     D, Wt = random_case(rng, 50, 400, np.float64)
     err = run_wa(lib, 1, po.ADD, 4, Wt.copy(), D, -99999.0, 1, 0)
+    assert err[0] > 0 or err[1] > 0
+
+
+def test_wa_deep_prefetch_needs_the_strict_order():
+    """cfg 5 loads two steps ahead on the ring of a one-step prefetch. That only works because the loads of a step go
+    out after its write-backs were read out; a ring three rows shorter must trip the hazard counters."""
+    lib = _build(extra=("-DWDPM_NRING_DELTA=-3",), name="libmw_emul_shrunk.so")
+    rng = np.random.default_rng(6)
+    D, Wt = random_case(rng, 60, 400, np.float64)
+    err = run_wa(lib, 5, po.ADD, 0, Wt.copy(), D, -99999.0, 1, 0)
     assert err[0] > 0 or err[1] > 0

@@ -188,6 +188,49 @@ __global__ void k_block_reduce_stage2(const BlockPartial* __restrict__ partials,
     }
 }
 
+// Order-free part of the final statistics (src/WDPMCL.c:1394-1459) over the interior cells this solver owns:
+// cells with dem > nodata (basincount, :1424-1431), of those the cells with more than 1 mm of water (watercount,
+// :1395-1422: `water > 0.001`), and the deepest water on a valid cell (maxdepth, :1451-1459). Integer counts
+// and a maximum do not depend on the order of evaluation; the volume sums of the report do (the reference adds
+// the cells one by one in double) and stay with the host, which has the grid for the output file anyway.
+struct FinalStats {
+    unsigned long long valid_cells;
+    unsigned long long wet_above_1mm;
+    double max_depth;
+};
+
+template <typename T>
+__global__ void k_final_stats(const T* __restrict__ w, const T* __restrict__ d, Geom g, int first_row, int n_rows, FinalStats* __restrict__ out) {
+    unsigned long long nvalid = 0, nwet = 0;
+    double md = -1.0e300;
+    for (int i = first_row + blockIdx.x; i < first_row + n_rows; i += gridDim.x) {
+        const size_t base = dev_index(g, i, 0);
+        for (int j = 1 + threadIdx.x; j <= g.C; j += blockDim.x) {
+            const T e = d[base + j];
+            if (is_valid_elevation(e) || is_outlet(e)) {  // a Drain outlet is a valid cell wearing a mark
+                const double v = (double)w[base + j];
+                nvalid++;
+                nwet += v > 0.001 ? 1ull : 0ull;
+                md = v > md ? v : md;
+            }
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        nvalid += __shfl_down_sync(0xffffffffu, nvalid, off);
+        nwet += __shfl_down_sync(0xffffffffu, nwet, off);
+        const double o = __shfl_down_sync(0xffffffffu, md, off);
+        md = o > md ? o : md;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (nvalid) atomicAdd(&out->valid_cells, nvalid);
+        if (nwet) atomicAdd(&out->wet_above_1mm, nwet);
+        // maximum of doubles through their order-preserving integer image (water depths are >= 0 here or the max is of negatives too)
+        long long bits = __double_as_longlong(md);
+        bits = bits >= 0 ? bits : (long long)(0x8000000000000000ull - (unsigned long long)bits);
+        atomicMax(reinterpret_cast<long long*>(&out->max_depth), bits);
+    }
+}
+
 // Order-free 64-bit checksum of the interior water cells this solver owns: sum over cells of
 // bits(w) * (2 * index + 1) modulo 2^64, index = the cell's position in the WHOLE DEM (row-major,
 // 0-based). Integer addition commutes, so stripes can be summed in any order and the result does not depend
@@ -690,9 +733,17 @@ __device__ __forceinline__ void data_movement_warp(const FusedParams<T>& p, cons
             // than the trip to HBM. The ring slots it overwrites belonged to rows written home by the store group
             // of step s - 2 (committed a whole step ago), which must have been read out: every group committed so
             // far. The rows of step s - 1, stored just below, lie elsewhere in the ring (mw_schedule.h, NRING_MIN).
-            if (s > 1) bulk_wait_read<0>();
-            if (s + PF < tile.n_steps) issue_row_loads<CFG, T>(p, tile, ring_w, ring_d, bars, s + PF);
-            if (s > 0) issue_row_stores<CFG, T>(p, tile, ring_w, s - 1);
+            if (CFG::STRICT_ORDER) {
+                // deep prefetch (mw_schedule.h, WaCfg::RING_PF): the rows loaded now take the place of the rows
+                // written home now, so the write-backs go first and must have read their rows out
+                if (s > 0) issue_row_stores<CFG, T>(p, tile, ring_w, s - 1);
+                bulk_wait_read<0>();
+                if (s + PF < tile.n_steps) issue_row_loads<CFG, T>(p, tile, ring_w, ring_d, bars, s + PF);
+            } else {
+                if (s > 1) bulk_wait_read<0>();
+                if (s + PF < tile.n_steps) issue_row_loads<CFG, T>(p, tile, ring_w, ring_d, bars, s + PF);
+                if (s > 0) issue_row_stores<CFG, T>(p, tile, ring_w, s - 1);
+            }
         }
         __syncwarp();
         WDPM_TL(1);
@@ -1052,15 +1103,20 @@ k_fused_wa(const FusedParams<T> p) {
     bool run = false;
 
     // first part of step s: window into registers, first colour sub-pass (and, staggered, half of the second)
+    // Loop-carried addressing: this warp's triple advances by NT per step, its first ring slot by 3*NT (mod NRING);
+    // `run` is one unsigned compare against the runnable range [m_lo, m_hi - (ph > 0)] (MwTile::runnable).
+    const int m_first = tile.m_lo - ph * CFG::LAG + t;               // triple of step 0 (may lie before the staged range)
+    const unsigned run_span = (unsigned)(tile.m_hi - (ph > 0 ? 1 : 0) - tile.m_lo);
+    int slot0 = (((3 * (m_first - tile.m_lo) + ph) % NRING) + NRING) % NRING;  // ring slot of row 3*m + ph at step 0
     auto begin_step = [&](int s) {
-        const int m = tile.m_lo + NT * s - ph * CFG::LAG + t;
-        run = tile.runnable(m, ph);
+        const int m = m_first + NT * s;
+        run = (unsigned)(m - tile.m_lo) <= run_span;
         WDPM_TL(0);
-        if (ph == 0 && tile.staged(m)) mbar_wait(&bars[s % NSTAGE], (uint32_t)((s / NSTAGE) & 1));
+        if (ph == 0 && run) mbar_wait(&bars[s % NSTAGE], (uint32_t)((s / NSTAGE) & 1));  // phase 0 runs exactly on the staged triples
         WDPM_TL(1);
+        const int s0 = slot0;
+        slot0 += 3 * NT; if (slot0 >= NRING) slot0 -= NRING;
         if (run) {
-            const int row0 = 3 * m + ph;
-            int s0 = tile.ring_slot(row0);
             int s1 = s0 + 1; if (s1 == NRING) s1 = 0;
             int s2 = s1 + 1; if (s2 == NRING) s2 = 0;
             wrow[0] = ring_w + s0 * W + cb; wrow[1] = ring_w + s1 * W + cb; wrow[2] = ring_w + s2 * W + cb;
@@ -1120,7 +1176,7 @@ k_fused_wa(const FusedParams<T> p) {
         for (int s = 0; s < tile.n_steps; s++) {
             begin_step(s);
             end_step(s);
-            fence_proxy_async();  // make this step's smem writes visible to the bulk-store engine
+            if (ph == NPH - 1) fence_proxy_async();  // the last phase's rows go home by bulk store: make them visible to the async proxy
             WDPM_TL(7);
             __syncthreads();
             WDPM_TL(8);
@@ -1134,7 +1190,7 @@ k_fused_wa(const FusedParams<T> p) {
             } else {
                 if (h > t && s < tile.n_steps) end_step(s);
             }
-            fence_proxy_async();
+            if (ph == NPH - 1) fence_proxy_async();
             __syncthreads();
         }
     }

@@ -67,6 +67,7 @@ struct MwCfg {
 #endif
     static constexpr int NRING = ((NRING_MIN + 2) / 3) * 3 + WDPM_NRING_DELTA;  // ring rows (multiple of 3)
     static constexpr int NSTAGE = PF + 1;      // load barriers
+    static constexpr bool STRICT_ORDER = false;
     static_assert(W % 4 == 0, "window rows must be 16-byte multiples");
     static_assert(TWV > 0, "window too narrow for its halos");
     static_assert(K >= 1 && K <= kMaxItersPerLaunch, "iterations per launch");
@@ -84,12 +85,21 @@ struct MwCfg {
 // lanes 0..30 finish and store the columns [2, 188) relative to the warp's start; consecutive warps start
 // WSTRIDE = 186 columns apart so that these ranges abut. The window's own edges lose 2 columns (left) and
 // 4 (right) per phase exactly as the halo analysis above says (8 and 16 over the three phases of an iteration).
-template <int KW_, int NT_, int PF_>
+// RING_PF < PF ("deep prefetch"): the ring is sized for a prefetch distance of RING_PF steps although loads go
+// out PF steps ahead. It works when the data-movement warp issues the loads of a step only AFTER the write-backs it
+// has just issued have read their rows out of shared memory (cp.async.bulk.wait_group.read 0 between the two): the
+// ring formula reserves 3*NT rows for a write-back that may still be reading while new rows land; with the strict
+// order those rows can take the extra step of prefetch instead. (PF = 2 on the PF = 1 ring: the rows loaded at step s
+// for step s+2 alias the rows stored at step s and nothing younger; the emulator's hazard counters check it.)
+template <int KW_, int NT_, int PF_, int RING_PF_ = PF_>
 struct WaCfg {
     static constexpr int KW = KW_;        // warps per row triple
     static constexpr int NT = NT_;        // row triples per phase per step
     static constexpr int K = 1;           // iterations per launch
     static constexpr int PF = PF_;        // prefetch distance in steps
+    static constexpr int RING_PF = RING_PF_;
+    static constexpr bool STRICT_ORDER = RING_PF_ < PF_;  // loads only after the step's write-backs were read out
+    static_assert(RING_PF_ == PF_ || RING_PF_ == PF_ - 1, "the strict order buys exactly one step of prefetch");
     static constexpr int NPH = 3;
     static constexpr int LAG = NT + 1;
     static constexpr int CPL = 6;                    // columns (two tiles) per lane
@@ -99,7 +109,7 @@ struct WaCfg {
     static constexpr int TWV = ((KW * WSTRIDE - 10 - HL) / 12) * 12;  // valid after three phases: [8, KW*WSTRIDE - 10)
     static constexpr int TOP_TRIPLES = 1;
     static constexpr int BOT_TRIPLES = 2;
-    static constexpr int NRING_MIN = 3 * NT * (PF + 2) + 3 * (NPH - 1) * LAG - 2;
+    static constexpr int NRING_MIN = 3 * NT * (RING_PF + 2) + 3 * (NPH - 1) * LAG - 2;
     static constexpr int NRING = ((NRING_MIN + 2) / 3) * 3 + WDPM_NRING_DELTA;
     static constexpr int NSTAGE = PF + 1;
     static constexpr int NWARPS = NPH * NT * KW;     // compute warps

@@ -159,6 +159,8 @@ const std::vector<FusedVariant<double>>& fused_variants<double>() {
         make_wa_variant<double, WaCfg<3, 1, 1>, kOptAddFast>(),                             // 21: 566-column window, one triple per phase (9 warps)
         make_wa_variant<double, WaCfg<2, 2, 1>, kOptAddFast | kOptRegRealloc | kOptStagger>(),  // 22: as 17, staggered: triple slot 1 half a step behind slot 0
         make_wa_variant<double, WaCfg<1, 2, 1>, kOptAddFast | kOptStagger>(),               // 23: test window for 22
+        make_wa_variant<double, WaCfg<2, 2, 2, 1>, kOptAddFast | kOptRegRealloc>(),         // 24: as 17, bulk loads two steps ahead on the same ring (strict order)
+        make_wa_variant<double, WaCfg<1, 1, 2, 1>, kOptAddFast>(),                          // 25: test window for 24
     };
     return v;
 }
@@ -186,6 +188,8 @@ const std::vector<FusedVariant<float>>& fused_variants<float>() {
         make_wa_variant<float, WaCfg<4, 2, 1>, kOptRegRealloc>(),  // 19: as 16 with the reference form of the step (comparison)
         make_wa_variant<float, WaCfg<4, 2, 1>, kOptAddFast | kOptRegRealloc | kOptStagger>(),  // 20: as 16, staggered
         make_wa_variant<float, WaCfg<1, 2, 1>, kOptAddFast | kOptStagger>(),               // 21: test window for 20
+        make_wa_variant<float, WaCfg<4, 2, 2, 1>, kOptAddFast | kOptRegRealloc>(),         // 22: as 16, bulk loads two steps ahead on the same ring
+        make_wa_variant<float, WaCfg<1, 1, 2, 1>, kOptAddFast>(),                          // 23: test window for 22
     };
     return v;
 }
@@ -1152,6 +1156,39 @@ int wdpm_get_cell_water(wdpm_solver* s, int32_t row, int32_t col, double* value)
                              cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     *value = s->dtype == WDPM_F64 ? v64 : (double)v32;
+    return WDPM_OK;
+}
+
+int wdpm_final_statistics(wdpm_solver* s, int64_t* valid_cells, int64_t* wet_above_1mm, double* max_depth) {
+    if (!s) return fail(WDPM_E_ARG, "null solver");
+    if (!s->have_dem) return fail(WDPM_E_STATE, "nothing uploaded yet");
+    if (s->in_block) return fail(WDPM_E_STATE, "a block is open");
+    CUDA_TRY(cudaSetDevice(s->device));
+    const int lo = s->stripe ? std::max(s->G, 1) - s->G : 1;
+    const int hi = s->stripe ? std::min(s->G + s->P, s->cfg.rows + 1) - s->G : s->g.R + 1;
+    FinalStats* d_st = reinterpret_cast<FinalStats*>(s->partials);  // scratch, free between blocks
+    FinalStats init{0ull, 0ull, 0.0};
+    const long long lowest = (long long)0x8000000000000000ull;  // image of the most negative double: below every depth
+    std::memcpy(&init.max_depth, &lowest, sizeof(lowest));
+    CUDA_TRY(cudaMemcpyAsync(d_st, &init, sizeof(init), cudaMemcpyHostToDevice, s->stream));
+    const int grid = std::max(1, std::min(hi - lo, s->sm_count * 8));
+    if (s->dtype == WDPM_F64)
+        k_final_stats<double><<<grid, 256, 0, s->stream>>>(static_cast<const double*>(s->w[s->cur]), static_cast<const double*>(s->dem), s->g, lo, hi - lo, d_st);
+    else
+        k_final_stats<float><<<grid, 256, 0, s->stream>>>(static_cast<const float*>(s->w[s->cur]), static_cast<const float*>(s->dem), s->g, lo, hi - lo, d_st);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    FinalStats out;
+    CUDA_TRY(cudaMemcpyAsync(&out, d_st, sizeof(out), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    long long bits;
+    std::memcpy(&bits, &out.max_depth, sizeof(bits));
+    bits = bits >= 0 ? bits : (long long)(0x8000000000000000ull - (unsigned long long)bits);  // the image is its own inverse
+    double md;
+    std::memcpy(&md, &bits, sizeof(md));
+    if (valid_cells) *valid_cells = (int64_t)out.valid_cells;
+    if (wet_above_1mm) *wet_above_1mm = (int64_t)out.wet_above_1mm;
+    if (max_depth) *max_depth = out.valid_cells ? md : 0.0;
     return WDPM_OK;
 }
 

@@ -842,22 +842,42 @@ static int run_module(int ntok, char tok[][512], int argc, chain_state *cs)
     /* final grid and statistics (WDPMCL.c:1379-1467) */
     set_download(&ss, water, cols);
     mark_nodata(water, dem, n, nodata);
+    /* The order-free statistics come from the device (wdpm_final_statistics: counts add and maxima combine over the
+     * stripes); the volume is the reference's own sequential sum over the grid the output file needs anyway, so that
+     * the printed digits are the reference's (WDPMCL.c:1394-1459). */
     long watercount = 0;
-    double watertotal = 0.0;
-    for (size_t i = 0; i < n; i++) {
-        if (dem[i] > nodata) {
-            watertotal += water[i];
-            if (water[i] > 0.001) watercount++;
-        }
+    double watertotal = 0.0, dev_maxdepth = 0.0;
+    int64_t dev_valid = 0, dev_wet = 0;
+    int have_dev_stats = 1;
+    for (int g = 0; g < ss.n; g++) {
+        int64_t nv = 0, nw = 0;
+        double md = 0.0;
+        if (wdpm_final_statistics(ss.sv[g], &nv, &nw, &md) != WDPM_OK) { have_dev_stats = 0; break; }
+        if (nv > 0 && (dev_valid == 0 || md > dev_maxdepth)) dev_maxdepth = md;
+        dev_valid += nv;
+        dev_wet += nw;
+    }
+    for (size_t i = 0; i < n; i++)
+        if (dem[i] > nodata) watertotal += water[i];
+    if (have_dev_stats && dev_valid == basincount && basincount > 0) {
+        watercount = (long)dev_wet;
+    } else { /* no valid cell, or a DEM the device masks differently (NaN / infinite elevations): count here */
+        have_dev_stats = 0;
+        for (size_t i = 0; i < n; i++)
+            if (dem[i] > nodata && water[i] > 0.001) watercount++;
     }
     const double final_vol = watertotal * cellarea;
     const double meanwater = watertotal / ((float)watercount);
     const double waterfrac = (float)watercount / (float)basincount;
     const double drainvol = total_drain * cellarea;
     const double draindepth = (drainvol / ((float)basincount * cellarea)) * 1000;
-    double maxdepth = water[0];
-    for (size_t i = 0; i < n; i++)
-        if (water[i] > maxdepth) maxdepth = water[i];
+    double maxdepth = water[0]; /* the reference scans every cell, NODATA-valued ones included (:1451-1459) */
+    if (have_dev_stats && nodata < 0 && dev_maxdepth >= maxdepth) {
+        maxdepth = dev_maxdepth; /* valid cells hold >= 0, NODATA cells the (negative) NODATA value: the maximum is a valid cell's */
+    } else {
+        for (size_t i = 0; i < n; i++)
+            if (water[i] > maxdepth) maxdepth = water[i];
+    }
     maxdepth *= 1000;
 
     line("                     ");

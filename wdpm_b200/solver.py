@@ -221,6 +221,13 @@ class Solver:
         _check(self._lib.wdpm_get_cell_water(self._h, C.c_int32(row), C.c_int32(col), C.byref(v)))
         return v.value
 
+    def final_statistics(self):
+        """(valid cells, cells with more than 1 mm of water, deepest water in m) over the owned interior cells -
+        the order-free part of the reference's final report (WDPMCL.c:1394-1459), computed on the device."""
+        nv, nw, md = C.c_int64(), C.c_int64(), C.c_double()
+        _check(self._lib.wdpm_final_statistics(self._h, C.byref(nv), C.byref(nw), C.byref(md)))
+        return nv.value, nw.value, md.value
+
     def water_checksum(self) -> int:
         """Order-free 64-bit checksum of the owned interior water cells (position-weighted bit patterns, mod 2^64)."""
         v = C.c_uint64()
