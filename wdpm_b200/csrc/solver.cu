@@ -210,6 +210,7 @@ struct wdpm_solver {
     int device = 0;
     // resident kernel tiling (kernels.cuh, k_resident); res_ok = the grid fits one co-resident wave
     bool res_ok = false;
+    bool resident_by_auto = false;  // AUTO picked the resident kernel: a refused cooperative launch falls back to the fused one
     int res_TR = 0, res_TC = 0, res_ntx = 0, res_nty = 0;
     size_t res_smem = 0;
 
@@ -455,10 +456,28 @@ cudaError_t launch_resident(wdpm_solver* s, int n) {
     p.launch_slot = s->launch_slot;
     p.ds = drain_state<T>(s);
     void* args[] = {&p};
-    auto kern = k_resident<T, MODULE, kResidentThreads>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->res_smem);
-    if (e != cudaSuccess) return e;
+    auto kern = k_resident<T, MODULE, kResidentThreads>;  // shared-memory limit set in wdpm_create (resident_fits)
     return cudaLaunchCooperativeKernel((void*)kern, dim3(s->res_ntx * s->res_nty), dim3(kResidentThreads), args, s->res_smem, s->stream);
+}
+
+// Can the whole grid of the resident kernel be co-resident (a cooperative launch needs it)? Also sets the
+// kernel's dynamic shared-memory limit once. Called from wdpm_create.
+template <typename T, int MODULE>
+bool resident_fits(const wdpm_solver* s) {
+    auto kern = k_resident<T, MODULE, kResidentThreads>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->res_smem) != cudaSuccess) { cudaGetLastError(); return false; }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kResidentThreads, s->res_smem) != cudaSuccess) { cudaGetLastError(); return false; }
+    return (long long)per_sm * s->sm_count >= (long long)s->res_ntx * s->res_nty;
+}
+
+template <typename T>
+bool resident_fits_module(const wdpm_solver* s) {
+    switch (s->module) {
+        case WDPM_ADD: return resident_fits<T, kAdd>(s);
+        case WDPM_SUBTRACT: return resident_fits<T, kSubtract>(s);
+        default: return resident_fits<T, kDrain>(s);
+    }
 }
 
 template <typename T>
@@ -469,6 +488,14 @@ int resident_iterations(wdpm_solver* s, int n) {
         case WDPM_ADD: e = launch_resident<T, kAdd>(s, n); break;
         case WDPM_SUBTRACT: e = launch_resident<T, kSubtract>(s, n); break;
         default: e = launch_resident<T, kDrain>(s, n); break;
+    }
+    if (e != cudaSuccess && s->resident_by_auto) {
+        // AUTO chose this kernel; the cooperative launch can still be refused at run time (GPU shared with other
+        // contexts, fewer SMs available): nothing has run, so fall back to the fused kernel for good
+        cudaGetLastError();
+        s->kernel = WDPM_KERNEL_FUSED;
+        s->resident_by_auto = false;
+        return fused_iterations<T>(s, n);
     }
     CUDA_TRY(e);
     s->launches++;
@@ -814,8 +841,9 @@ int wdpm_create(const wdpm_config* cfg, wdpm_solver** out) {
             s->res_ok = s->res_smem <= 200 * 1024 && best <= 9ll * 4 * kResidentThreads && cells <= (1ll << 21);
         }
     }
+    if (s->res_ok) s->res_ok = s->dtype == WDPM_F64 ? resident_fits_module<double>(s) : resident_fits_module<float>(s);
     if (cfg->kernel == WDPM_KERNEL_RESIDENT && !s->res_ok) { delete s; return fail(WDPM_E_UNSUPPORTED, "grid too large (or device unsuitable) for the resident kernel"); }
-    if (cfg->kernel == WDPM_KERNEL_AUTO && s->res_ok && cells <= (1ll << 20)) s->kernel = WDPM_KERNEL_RESIDENT;
+    if (cfg->kernel == WDPM_KERNEL_AUTO && s->res_ok && cells <= (1ll << 20)) { s->kernel = WDPM_KERNEL_RESIDENT; s->resident_by_auto = true; }
 
     auto cleanup = [&](int code, const std::string& msg) {
         wdpm_destroy(s);
