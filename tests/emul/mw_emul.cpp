@@ -199,7 +199,7 @@ int run_launches(T* w_padded, const T* d_padded, int R, int C, T nodata, int n_l
 // stores nothing, shuffles take the right-hand lane's value (lane 31 keeps its own).
 template <typename T, int MODULE, typename CFG, bool FAST, bool GUARD>
 void run_cta_wa(const Layout& L, const T* w_in, T* w_out, const T* dem, int strip, int chunk,
-                int chunk_triples, int total_triples, Errors& err, std::vector<unsigned char>& stored_mask) {
+                int chunk_triples, int total_triples, Errors& err, std::vector<unsigned char>& stored_mask, Event<T>* events = nullptr) {
     constexpr int W = CFG::W, NT = CFG::NT, NPH = CFG::NPH, NRING = CFG::NRING, PF = CFG::PF, KW = CFG::KW;
     MwTile<CFG> tile;
     tile.init(strip, chunk, chunk_triples, total_triples);
@@ -261,13 +261,39 @@ void run_cta_wa(const Layout& L, const T* w_in, T* w_out, const T* dem, int stri
                 }
             for (int kw = 0; kw < KW; kw++) {
                 Lane* wl = &lanes[(size_t)kw * 32];
-                for (int lane = 0; lane < 32; lane++) wa_relax_pair<T, MODULE, 0, FAST, GUARD>(wl[lane].wt, wl[lane].dd);
+                // Drain: a warp with an outlet mark in any lane's window takes the outlet path (the kernel's __any_sync)
+                bool near = false;
+                if (MODULE == kDrain)
+                    for (int lane = 0; lane < 32; lane++)
+                        for (int r = 0; r < 3; r++)
+                            for (int c = 0; c < 8; c++) near = near || is_outlet(wl[lane].dd[r][c]);
+                const int crow = row0 + 1;
+                auto sub = [&](auto c_tag) {
+                    constexpr int CC = decltype(c_tag)::value;
+                    for (int lane = 0; lane < 32; lane++) {
+                        if (MODULE == kDrain && near) {
+                            const int cb = CFG::WSTRIDE * kw + CFG::CPL * lane;
+                            wa_relax_pair_outlets<T, CC, FAST>(wl[lane].wt, wl[lane].dd, [&](int tl, int a, int b, T wo, T wc) {
+                                (void)a; (void)b;
+                                const int ccol = tile.x0 + cb + CC + 3 * tl + 1;
+                                if (lane < 31 && tile.owns_row(crow) && tile.owns_col(ccol) && events) {
+                                    Event<T>& e = events[ph * 3 + CC];
+                                    if (e.valid) err.double_store++;  // one contact per outlet and sub-pass
+                                    e.w_outlet = wo; e.w_centre = wc; e.valid = 1;
+                                }
+                            });
+                        } else {
+                            wa_relax_pair<T, MODULE, CC, FAST, GUARD>(wl[lane].wt, wl[lane].dd);
+                        }
+                    }
+                };
+                sub(std::integral_constant<int, 0>{});
                 for (int lane = 0; lane < 32; lane++)
                     for (int r = 0; r < 3; r++) wl[lane].wt[r][6] = wl[lane < 31 ? lane + 1 : lane].wt[r][0];
-                for (int lane = 0; lane < 32; lane++) wa_relax_pair<T, MODULE, 1, FAST, GUARD>(wl[lane].wt, wl[lane].dd);
+                sub(std::integral_constant<int, 1>{});
                 for (int lane = 0; lane < 32; lane++)
                     for (int r = 0; r < 3; r++) wl[lane].wt[r][7] = wl[lane < 31 ? lane + 1 : lane].wt[r][1];
-                for (int lane = 0; lane < 32; lane++) wa_relax_pair<T, MODULE, 2, FAST, GUARD>(wl[lane].wt, wl[lane].dd);
+                sub(std::integral_constant<int, 2>{});
             }
             for (int kw = 0; kw < KW; kw++)
                 for (int lane = 0; lane < 31; lane++) {
@@ -458,7 +484,8 @@ void run_cta_wa_stag(const Layout& L, const T* w_in, T* w_out, const T* dem, int
 }
 
 template <typename T, int MODULE, typename CFG, bool FAST, bool GUARD>
-int run_launches_wa(T* w_padded, const T* d_padded, int R, int C, T nodata, int n_launches, int chunk_triples, long long* err_out, bool stag) {
+int run_launches_wa(T* w_padded, const T* d_padded, int R, int C, T nodata, int n_launches, int chunk_triples, long long* err_out, bool stag,
+                    int drainrow = -10, int draincol = -10, T* totaldrain = nullptr) {
     Layout L;
     L.R = R; L.C = C;
     const int n_strips = (C + 2 + CFG::TWV - 1) / CFG::TWV;
@@ -474,22 +501,28 @@ int run_launches_wa(T* w_padded, const T* d_padded, int R, int C, T nodata, int 
             dem[L.at(i, j)] = mask_elevation(d_padded[(size_t)i * (C + 2) + j], nodata);
             wa[L.at(i, j)] = w_padded[(size_t)i * (C + 2) + j];
         }
+    if (MODULE == kDrain && drainrow >= 0 && drainrow <= R + 1 && draincol >= 0 && draincol <= C + 1)
+        dem[L.at(drainrow, draincol)] = outlet_mark<T>();  // as the solver marks an outlet (relax.cuh)
     Errors err;
     T* cur = wa.data();
     T* nxt = wb.data();
+    T td = totaldrain ? *totaldrain : T(0);
     for (int l = 0; l < n_launches; l++) {
+        std::vector<Event<T>> events(9, Event<T>{T(0), T(0), 0});
         std::vector<unsigned char> stored(n, 0);
         for (int chunk = 0; chunk < n_chunks; chunk++)
             for (int strip = 0; strip < n_strips; strip++)
                 if constexpr (CFG::NT == 2) {
                     if (stag) run_cta_wa_stag<T, MODULE, CFG, FAST, GUARD>(L, cur, nxt, dem.data(), strip, chunk, chunk_triples, total_triples, err, stored);
-                    else run_cta_wa<T, MODULE, CFG, FAST, GUARD>(L, cur, nxt, dem.data(), strip, chunk, chunk_triples, total_triples, err, stored);
+                    else run_cta_wa<T, MODULE, CFG, FAST, GUARD>(L, cur, nxt, dem.data(), strip, chunk, chunk_triples, total_triples, err, stored, events.data());
                 } else {
-                    run_cta_wa<T, MODULE, CFG, FAST, GUARD>(L, cur, nxt, dem.data(), strip, chunk, chunk_triples, total_triples, err, stored);
+                    run_cta_wa<T, MODULE, CFG, FAST, GUARD>(L, cur, nxt, dem.data(), strip, chunk, chunk_triples, total_triples, err, stored, events.data());
                 }
         for (int i = 0; i < R + 2; i++)
             for (int j = 0; j < C + 2; j++)
                 if (!stored[L.at(i, j)]) err.unstored++;
+        for (auto& e : events)
+            if (e.valid) { td = td + e.w_outlet; td = td + e.w_centre; }
         T* tmp = cur; cur = nxt; nxt = tmp;
     }
     long long margin_dirty = 0;
@@ -502,6 +535,7 @@ int run_launches_wa(T* w_padded, const T* d_padded, int R, int C, T nodata, int 
     }
     for (int i = 0; i < R + 2; i++)
         for (int j = 0; j < C + 2; j++) w_padded[(size_t)i * (C + 2) + j] = cur[L.at(i, j)];
+    if (totaldrain) *totaldrain = td;
     err_out[0] = err.wrong_row;
     err_out[1] = err.load_over_store;
     err_out[2] = err.double_store;
@@ -512,7 +546,7 @@ int run_launches_wa(T* w_padded, const T* d_padded, int R, int C, T nodata, int 
 
 // mode: bit 0 = fast Add step, bit 1 = no activity guard (Add on a clean grid only), bit 2 = staggered schedule (NT = 2)
 template <typename T, typename CFG>
-int dispatch_wa(int module, int mode, T* w, const T* d, int R, int C, T nodata, int n, int ct, long long* e) {
+int dispatch_wa(int module, int mode, T* w, const T* d, int R, int C, T nodata, int n, int ct, long long* e, int dr = -10, int dc = -10, T* td = nullptr) {
     const bool stag = (mode & 4) != 0;
     if (stag && CFG::NT != 2) return -3;
     mode &= 3;
@@ -520,19 +554,23 @@ int dispatch_wa(int module, int mode, T* w, const T* d, int R, int C, T nodata, 
     if (module == kAdd && mode == 1) return run_launches_wa<T, kAdd, CFG, true, true>(w, d, R, C, nodata, n, ct, e, stag);
     if (module == kAdd) return run_launches_wa<T, kAdd, CFG, false, true>(w, d, R, C, nodata, n, ct, e, stag);
     if (module == kSubtract) return run_launches_wa<T, kSubtract, CFG, false, true>(w, d, R, C, nodata, n, ct, e, stag);
+    if (module == kDrain && !stag) {
+        if (mode & 1) return run_launches_wa<T, kDrain, CFG, true, true>(w, d, R, C, nodata, n, ct, e, false, dr, dc, td);
+        return run_launches_wa<T, kDrain, CFG, false, true>(w, d, R, C, nodata, n, ct, e, false, dr, dc, td);
+    }
     return -1;
 }
 
 template <typename T>
-int dispatch_wa_cfg(int cfg, int module, int mode, T* w, const T* d, int R, int C, T nodata, int n, int ct, long long* e) {
+int dispatch_wa_cfg(int cfg, int module, int mode, T* w, const T* d, int R, int C, T nodata, int n, int ct, long long* e, int dr = -10, int dc = -10, T* td = nullptr) {
     switch (cfg) {
-        case 0: return dispatch_wa<T, WaCfg<1, 1, 1>>(module, mode, w, d, R, C, nodata, n, ct, e);
-        case 1: return dispatch_wa<T, WaCfg<2, 2, 1>>(module, mode, w, d, R, C, nodata, n, ct, e);
-        case 2: return dispatch_wa<T, WaCfg<2, 1, 2>>(module, mode, w, d, R, C, nodata, n, ct, e);
-        case 3: return dispatch_wa<T, WaCfg<3, 1, 1>>(module, mode, w, d, R, C, nodata, n, ct, e);
-        case 4: return dispatch_wa<T, WaCfg<1, 2, 1>>(module, mode, w, d, R, C, nodata, n, ct, e);
-        case 5: return dispatch_wa<T, WaCfg<2, 2, 2, 1>>(module, mode, w, d, R, C, nodata, n, ct, e);
-        case 6: return dispatch_wa<T, WaCfg<1, 1, 2, 1>>(module, mode, w, d, R, C, nodata, n, ct, e);
+        case 0: return dispatch_wa<T, WaCfg<1, 1, 1>>(module, mode, w, d, R, C, nodata, n, ct, e, dr, dc, td);
+        case 1: return dispatch_wa<T, WaCfg<2, 2, 1>>(module, mode, w, d, R, C, nodata, n, ct, e, dr, dc, td);
+        case 2: return dispatch_wa<T, WaCfg<2, 1, 2>>(module, mode, w, d, R, C, nodata, n, ct, e, dr, dc, td);
+        case 3: return dispatch_wa<T, WaCfg<3, 1, 1>>(module, mode, w, d, R, C, nodata, n, ct, e, dr, dc, td);
+        case 4: return dispatch_wa<T, WaCfg<1, 2, 1>>(module, mode, w, d, R, C, nodata, n, ct, e, dr, dc, td);
+        case 5: return dispatch_wa<T, WaCfg<2, 2, 2, 1>>(module, mode, w, d, R, C, nodata, n, ct, e, dr, dc, td);
+        case 6: return dispatch_wa<T, WaCfg<1, 1, 2, 1>>(module, mode, w, d, R, C, nodata, n, ct, e, dr, dc, td);
     }
     return -2;
 }
@@ -603,6 +641,14 @@ int wa_emul_run_f64(int cfg, int module, int mode, double* w, const double* d, i
 int wa_emul_run_f32(int cfg, int module, int mode, float* w, const float* d, int R, int C, float nodata, int n_launches,
                     int chunk_triples, long long* errors5) {
     return dispatch_wa_cfg<float>(cfg, module, mode, w, d, R, C, nodata, n_launches, chunk_triples, errors5);
+}
+int wa_emul_drain_f64(int cfg, int mode, double* w, const double* d, int R, int C, double nodata, int n_launches, int chunk_triples,
+                      int drainrow, int draincol, double* totaldrain, long long* errors5) {
+    return dispatch_wa_cfg<double>(cfg, kDrain, mode, w, d, R, C, nodata, n_launches, chunk_triples, errors5, drainrow, draincol, totaldrain);
+}
+int wa_emul_drain_f32(int cfg, int mode, float* w, const float* d, int R, int C, float nodata, int n_launches, int chunk_triples,
+                      int drainrow, int draincol, float* totaldrain, long long* errors5) {
+    return dispatch_wa_cfg<float>(cfg, kDrain, mode, w, d, R, C, nodata, n_launches, chunk_triples, errors5, drainrow, draincol, totaldrain);
 }
 int mw_emul_run_f32(int cfg, int module, float* w, const float* d, int R, int C, float nodata, int n_launches,
                     int chunk_triples, int drainrow, int draincol, float* totaldrain, long long* errors5) {

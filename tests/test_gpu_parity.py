@@ -239,9 +239,10 @@ def _outlet_set(D, rng, twv):
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
-@pytest.mark.parametrize("kernel,variant", [(1, 0), (2, 1), (2, 2), (2, 3), (3, 0)])
+@pytest.mark.parametrize("kernel,variant", [(1, 0), (2, 1), (2, 2), (2, 3), (3, 0), (2, 17), (2, 18)])
 def test_drain_outlet_set_matches_oracle(cuda_lib, oracle, dt, kernel, variant):
-    """Extension (BASELINE configs[4]): a set of outlets. Water grid and every outlet's total, bit for bit."""
+    """Extension (BASELINE configs[4]): a set of outlets. Water grid and every outlet's total, bit for bit
+    (variants 17 / 18: the warp-autonomous kernel's outlet path)."""
     from wdpm_b200 import F32, F64, Solver, solver
     code = F64 if dt == np.float64 else F32
     twv = solver.fused_variant_info(2, code)["strip_cols"]
@@ -463,9 +464,8 @@ def test_basin5_add_300mm_to_convergence(cuda_lib, basin5, tmp_path):
 
 
 def test_auto_picks_the_production_tilings(cuda_lib):
-    """AUTO on a grid above the small-grid limit: Add/Subtract get the warp-autonomous kernel (fp64: 12 warps on a
-    380-column window; fp32: 24 warps on 752 columns), Drain keeps k_fused (fp64: the 16-warp tiling, folded-gate
-    step only with a zero threshold > 0; fp32: the 484-column one)."""
+    """AUTO on a grid above the small-grid limit: every module gets the warp-autonomous kernel (fp64: 12 warps on a
+    380-column window; fp32: 24 warps on 752 columns)."""
     from wdpm_b200 import F32, F64, Solver, solver
     from wdpm_b200.solver import PRODUCTION_FUSED_VARIANT_F32, PRODUCTION_FUSED_VARIANT_F64
     rows = cols = 2100  # 4.4 M cells
@@ -476,11 +476,9 @@ def test_auto_picks_the_production_tilings(cuda_lib):
     def variant(v, dtype):
         i = solver.fused_variant_info(v, dtype)
         return {k: i[k] for k in ("window_cols", "strip_cols", "cta_threads", "smem_bytes")}
-    assert tiling(0, F64, 5e-6) == (variant(PRODUCTION_FUSED_VARIANT_F64, F64), 1)
-    assert tiling(1, F64, 5e-6) == (variant(PRODUCTION_FUSED_VARIANT_F64, F64), 1)
-    assert tiling(2, F64, 5e-6) == (variant(15, F64), 0) and variant(15, F64) == variant(14, F64)   # same tiling, different Drain step
-    assert tiling(0, F32, 5e-6) == (variant(PRODUCTION_FUSED_VARIANT_F32, F32), 1)
-    assert tiling(2, F32, 5e-6) == (variant(12, F32), 0)
+    for module in (0, 1, 2):
+        assert tiling(module, F64, 5e-6) == (variant(PRODUCTION_FUSED_VARIANT_F64, F64), 1)
+        assert tiling(module, F32, 5e-6) == (variant(PRODUCTION_FUSED_VARIANT_F32, F32), 1)
 
 
 def test_tier2_parity_against_the_serial_path(cuda_lib, basin5):

@@ -22,8 +22,8 @@ NODATA = -99999.0
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
 @pytest.mark.parametrize("module", [0, 1, 2])
-@pytest.mark.parametrize("n_stripes", [2, 3])
-def test_in_process_stripes_match_single_solver(cuda_lib, oracle, dt, module, n_stripes):
+@pytest.mark.parametrize("n_stripes,variant", [(2, 2), (3, 2), (2, 18)])
+def test_in_process_stripes_match_single_solver(cuda_lib, oracle, dt, module, n_stripes, variant):
     from wdpm_b200 import F32, F64, KERNEL_FUSED, Solver
     from wdpm_b200.stripes import StripeSolver, connect_in_process, plan_stripes
     code = F64 if dt == np.float64 else F32
@@ -37,7 +37,7 @@ def test_in_process_stripes_match_single_solver(cuda_lib, oracle, dt, module, n_
     td_ref = oracle.iterate(ref, D, NODATA, module, n_it, outlet=outlet, totaldrain=0.5)
 
     plan = plan_stripes(rows, n_stripes)
-    ss = [StripeSolver(rows, cols, NODATA, module, st, dtype=code, fused_variant=2, fused_chunk_rows=21) for st in plan]
+    ss = [StripeSolver(rows, cols, NODATA, module, st, dtype=code, fused_variant=variant, fused_chunk_rows=21) for st in plan]
     connect_in_process(ss)
     for s, st in zip(ss, plan):
         s.upload_band(dem[st.band_row0:st.band_row0 + st.band_rows], w0[st.band_row0:st.band_row0 + st.band_rows])
@@ -62,8 +62,8 @@ def test_in_process_stripes_match_single_solver(cuda_lib, oracle, dt, module, n_
         assert dt(td) == dt(td_ref)
 
 
-@pytest.mark.parametrize("n_stripes", [2, 3])
-def test_in_process_stripes_with_an_outlet_set(cuda_lib, oracle, n_stripes):
+@pytest.mark.parametrize("n_stripes,variant", [(2, 2), (3, 2), (2, 18), (3, 18)])
+def test_in_process_stripes_with_an_outlet_set(cuda_lib, oracle, n_stripes, variant):
     """Outlet sets across stripes: outlets on and next to stripe borders; the water grid and every outlet's total
     are bit-exact (an outlet's total lives on the stripe that owns its row)."""
     from wdpm_b200 import F64
@@ -79,7 +79,7 @@ def test_in_process_stripes_with_an_outlet_set(cuda_lib, oracle, n_stripes):
     n_it = 6
     ref = W.copy()
     td_ref = oracle.iterate_outlets(ref, D, NODATA, n_it, outlets)
-    ss = [StripeSolver(rows, cols, NODATA, 2, st, dtype=F64, fused_variant=2, fused_chunk_rows=21) for st in plan]
+    ss = [StripeSolver(rows, cols, NODATA, 2, st, dtype=F64, fused_variant=variant, fused_chunk_rows=21) for st in plan]
     connect_in_process(ss)
     for s, st in zip(ss, plan):
         s.upload_band(dem[st.band_row0:st.band_row0 + st.band_rows], w0[st.band_row0:st.band_row0 + st.band_rows])

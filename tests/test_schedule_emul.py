@@ -199,3 +199,31 @@ def test_wa_deep_prefetch_needs_the_strict_order():
     D, Wt = random_case(rng, 60, 400, np.float64)
     err = run_wa(lib, 5, po.ADD, 0, Wt.copy(), D, -99999.0, 1, 0)
     assert err[0] > 0 or err[1] > 0
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_wa_drain_is_bit_exact(oracle, emul, dt):
+    """Drain in the warp-autonomous schedule: warps with an outlet mark in reach take the outlet walk (runoff.cl:104-111),
+    contacts are recorded once - by a storing lane of the CTA that owns the centre - and fold in sub-pass order.
+    Outlets on strip borders, warp borders (window column 186 of a two-warp row triple), chunk borders and the rim."""
+    rng = np.random.default_rng(91)
+    W_, TWV = C.c_int(), C.c_int()
+    for cfg in (0, 1):
+        emul.wa_emul_cfg_info(cfg, C.byref(W_), C.byref(TWV))
+        twv = TWV.value
+        rows, cols = 36, twv + 60
+        spots = [(15, twv), (15, twv - 1), (16, twv + 1), (1, 1), (rows, cols), (12, 186 - 12 + 1), (13, 186 - 12), (18, 7), (21, twv + 30)]
+        for orow, ocol in spots:
+            for mode in (0, 1):
+                D, Wt = random_case(rng, rows, cols, dt, nodata_fraction=0.02, wet_fraction=0.95)
+                D[orow, ocol] = dt(480.0)
+                a, b = Wt.copy(), Wt.copy()
+                ta = oracle.iterate(a, D, -99999.0, po.DRAIN, 4, outlet=(orow, ocol), totaldrain=1.0)
+                sfx, ct = ("_f64", C.c_double) if dt == np.float64 else ("_f32", C.c_float)
+                tdv = np.array([1.0], dtype=dt)
+                err = np.zeros(5, dtype=np.int64)
+                rc = getattr(emul, "wa_emul_drain" + sfx)(cfg, mode, b.ctypes.data_as(C.c_void_p), D.ctypes.data_as(C.c_void_p), rows, cols, ct(-99999.0),
+                                                          4, 5, orow, ocol, tdv.ctypes.data_as(C.c_void_p), err.ctypes.data_as(C.c_void_p))
+                assert rc == 0 and not err.any(), (cfg, orow, ocol, mode, err)
+                assert np.array_equal(a, b), (cfg, orow, ocol, mode, int((a != b).sum()))
+                assert dt(ta) == tdv[0], (cfg, orow, ocol, mode)

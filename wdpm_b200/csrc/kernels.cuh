@@ -389,6 +389,30 @@ __global__ void k_mark_outlets(T* __restrict__ d, Geom g, const int* __restrict_
     else { saved[k] = d[a]; d[a] = outlet_mark<T>(); }
 }
 
+// Record one contact of a centre with the outlet at padded (orow, ocol): its two addends go into slot
+// (outlet, sub-pass `slot`) of event buffer `buffer` of the stripe that owns the outlet's row, to be folded in
+// sub-pass order (fold_events). `direct` (colour kernel: one launch per sub-pass, a single writer per outlet) adds
+// them to the total at once.
+template <typename T>
+__device__ __forceinline__ void record_contact(const DrainState<T>& ds, int buffer, int slot, int orow, int ocol, T w_outlet, T w_centre, bool direct) {
+    const int k = outlet_index(ds, orow, ocol);
+    if (k < 0) return;
+    if (direct) {
+        T td = ds.totaldrain[k];
+        td = td + w_outlet;
+        td = td + w_centre;
+        ds.totaldrain[k] = td;
+        return;
+    }
+    DrainEvent<T>* base = ds.events;
+    if (ds.events_up && orow < 0) base = ds.events_up;
+    else if (ds.events_dn && orow >= ds.P) base = ds.events_dn;
+    DrainEvent<T>* ev = event_slot(base, ds.n_outlets, buffer, k, slot);
+    ev->w_outlet = w_outlet;
+    ev->w_centre = w_centre;
+    ev->valid = 1;
+}
+
 // A Drain tile whose 3x3 holds outlets (rare): relax it in place and record the contacts. Out of line
 // so that its arrays live on the stack of this call only. `owner`: this CTA owns the centre, so it
 // reports the events (halo copies recompute the same contacts). `slot`: sub-pass slot in the buffer.
@@ -400,26 +424,8 @@ __device__ __noinline__ void drain_tile_near_outlets(T* w0, T* w1, T* w2, const 
     int pos[8];
     const int n = relax_tile_near_outlets<T>(w0, w1, w2, d0, d1, d2, j, mask, evo, evc, pos);
     if (!owner) return;
-    for (int i = 0; i < n; i++) {
-        const int orow = crow + pos[i] / 3 - 1;
-        const int k = outlet_index(ds, orow, ccol + pos[i] % 3 - 1);
-        if (k < 0) continue;
-        if (direct) {  // colour kernel: one launch per sub-pass, a single writer per outlet
-            T td = ds.totaldrain[k];
-            td = td + evo[i];
-            td = td + evc[i];
-            ds.totaldrain[k] = td;
-        } else {
-            // the stripe that owns the outlet's row keeps its total
-            DrainEvent<T>* base = ds.events;
-            if (ds.events_up && orow < 0) base = ds.events_up;
-            else if (ds.events_dn && orow >= ds.P) base = ds.events_dn;
-            DrainEvent<T>* ev = event_slot(base, ds.n_outlets, buffer, k, slot);
-            ev->w_outlet = evo[i];
-            ev->w_centre = evc[i];
-            ev->valid = 1;
-        }
-    }
+    for (int i = 0; i < n; i++)
+        record_contact<T>(ds, buffer, slot, crow + pos[i] / 3 - 1, ccol + pos[i] % 3 - 1, evo[i], evc[i], direct);
 }
 
 // ---------------------------------------------------------------------------
@@ -1050,10 +1056,12 @@ k_fused_wa(const FusedParams<T> p) {
     constexpr int kComputeRegs = kComputeRegsRaw > 232 ? 232 : kComputeRegsRaw;
     static_assert(!REALLOC || (MINB == 1 && NTHREADS % 128 == 0 && kComputeRegs > kLaunchRegs), "register reallocation needs whole warp groups, one CTA per SM");
     constexpr int W = CFG::W, NT = CFG::NT, NPH = CFG::NPH, NRING = CFG::NRING, NSTAGE = CFG::NSTAGE, KW = CFG::KW;
-    constexpr bool FAST = (OPT & kOptAddFast) && MODULE == kAdd;  // fp64: push_add_fast, fp32: push_add_nocap
-    constexpr bool GUARD = !(FAST && (OPT & kOptNoGuard));
+    // the cheaper forms of the step: Add - fp64 push_add_fast, fp32 push_add_nocap; Drain (fp64) - push_drain_fast
+    constexpr bool FAST = ((OPT & kOptAddFast) && MODULE == kAdd) || ((OPT & kOptDrainFast) && MODULE == kDrain && sizeof(T) == 8);
+    constexpr bool GUARD = !(FAST && MODULE == kAdd && (OPT & kOptNoGuard));
     constexpr bool STAGGER = (OPT & kOptStagger) != 0;
     static_assert(!STAGGER || CFG::NT == 2, "the staggered schedule splits a step by triple slot");
+    static_assert(!(STAGGER && MODULE == kDrain), "Drain runs the plain schedule (its outlet path is not split in halves)");
     using V2 = typename Vec2<T>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* ring_w = reinterpret_cast<T*>(smem_raw);
@@ -1067,12 +1075,26 @@ k_fused_wa(const FusedParams<T> p) {
     MwTile<CFG> tile;
     tile.init(strip, chunk, p.chunk_triples, p.total_triples);
 
+    if (MODULE == kDrain && blockIdx.x == 0) fold_events(p.ds, prev_event_slot(p.launch_slot), tid, NALL);
+
+    // Drain: does any outlet lie in the rows and columns this CTA stages? (If not, no window of this CTA can hold an
+    // outlet mark and the per-step test is skipped.)
+    __shared__ int s_cta_has_outlets;
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; i++) mbar_init(&bars[i], 1);
         for (int i = 0; i < NPH * NT; i++) mbar_init(&group_bars[i], KW);
         fence_mbar_init();
+        s_cta_has_outlets = 0;
     }
     __syncthreads();
+    if (MODULE == kDrain) {
+        for (int k = tid; k < p.ds.n_outlets; k += NALL) {
+            const int orow = p.ds.outlet_rc[2 * k], ocol = p.ds.outlet_rc[2 * k + 1];
+            if (orow >= 3 * tile.m_lo && orow <= 3 * tile.m_hi + 2 && ocol >= tile.x0 && ocol < tile.x0 + W) s_cta_has_outlets = 1;
+        }
+        __syncthreads();
+    }
+    const bool cta_has_outlets = MODULE == kDrain && s_cta_has_outlets != 0;
 
     if (tid >= NTHREADS) {
         if (REALLOC) {
@@ -1101,6 +1123,30 @@ k_fused_wa(const FusedParams<T> p) {
     T wt[3][8], dd[3][8];
     T* wrow[3] = {ring_w, ring_w, ring_w};
     bool run = false;
+    bool near_outlets = false;  // Drain: some lane of this warp holds an outlet mark in its window this step
+    int crow = 0;               // padded row of this step's centres
+
+    // One colour sub-pass of this lane's two tiles. Drain warps with an outlet in reach take the outlet path: the
+    // walk with the outlet rule, contacts recorded by the lane that will store the centre (lanes 0..30 of the CTA
+    // that owns it - lane 31 and the halo columns only hold copies).
+    auto subpass = [&](auto c_tag, auto part_tag) {
+        constexpr int C = decltype(c_tag)::value;
+        constexpr int PART = decltype(part_tag)::value;
+        if (MODULE == kDrain && near_outlets) {
+            if constexpr (MODULE == kDrain) {
+                wa_relax_pair_outlets<T, C, FAST>(wt, dd, [&](int tl, int a, int b, T w_outlet, T w_centre) {
+                    const int ccol = tile.x0 + cb + C + 3 * tl + 1;
+                    if (stores && tile.owns_row(crow) && tile.owns_col(ccol))
+                        record_contact<T>(p.ds, p.launch_slot, ph * 3 + C, crow + a, ccol + b, w_outlet, w_centre, false);
+                });
+            }
+        } else {
+            wa_relax_pair<T, MODULE, C, FAST, GUARD, PART>(wt, dd);
+        }
+    };
+    using I0 = std::integral_constant<int, 0>;
+    using I1 = std::integral_constant<int, 1>;
+    using I2 = std::integral_constant<int, 2>;
 
     // first part of step s: window into registers, first colour sub-pass (and, staggered, half of the second)
     // Loop-carried addressing: this warp's triple advances by NT per step, its first ring slot by 3*NT (mod NRING);
@@ -1133,7 +1179,19 @@ k_fused_wa(const FusedParams<T> p) {
                     dd[r][2 * v] = x.x; dd[r][2 * v + 1] = x.y;
                 }
             }
-            wa_relax_pair<T, MODULE, 0, FAST, GUARD>(wt, dd);
+            if (MODULE == kDrain) {
+                crow = 3 * m + ph + 1;
+                bool mine = false;
+                if (cta_has_outlets) {
+#pragma unroll
+                    for (int r = 0; r < 3; r++) {
+#pragma unroll
+                        for (int c = 0; c < 8; c++) mine = mine || is_outlet(dd[r][c]);
+                    }
+                }
+                near_outlets = cta_has_outlets && __any_sync(0xffffffffu, mine);
+            }
+            subpass(I0{}, I0{});
             WDPM_TL(2);
         }
         // every lane's window is in registers (the relax above consumed it): tell the row group. A group that
@@ -1143,18 +1201,18 @@ k_fused_wa(const FusedParams<T> p) {
         if (run) {
 #pragma unroll
             for (int r = 0; r < 3; r++) wt[r][6] = shfl_from_right(wt[r][0]);
-            if (STAGGER) wa_relax_pair<T, MODULE, 1, FAST, GUARD, 1>(wt, dd);
+            if (STAGGER) subpass(I1{}, I1{});
         }
     };
     // the rest of step s, and the write-back
     auto end_step = [&](int s) {
         if (run) {
-            if (STAGGER) wa_relax_pair<T, MODULE, 1, FAST, GUARD, 2>(wt, dd);
-            else wa_relax_pair<T, MODULE, 1, FAST, GUARD>(wt, dd);
+            if (STAGGER) subpass(I1{}, I2{});
+            else subpass(I1{}, I0{});
             WDPM_TL(3);
 #pragma unroll
             for (int r = 0; r < 3; r++) wt[r][7] = shfl_from_right(wt[r][1]);
-            wa_relax_pair<T, MODULE, 2, FAST, GUARD>(wt, dd);
+            subpass(I2{}, I0{});
             WDPM_TL(4);
             // the neighbouring warps of this row triple read columns I am about to overwrite: they must hold them by now
             if (KW > 1) mbar_wait(gbar, (uint32_t)(s & 1));

@@ -424,4 +424,45 @@ WDPM_RARE int relax_tile_near_outlets(T* w0, T* w1, T* w2, const T* d0, const T*
     return n;
 }
 
+// Warp-autonomous kernel, Drain, a lane whose 3 x 8 elevation window holds outlet marks (rare): the two tiles of
+// sub-pass C relaxed one after the other with the outlet rule of runoffdrain (src/runoff.cl:104-111: the outlet
+// test precedes the height test; both cells are emptied into the outlet's total and the walk goes on) and the
+// centre guard of src/runoff.cl:177-179 (an outlet is never a centre). Every contact is handed to
+// on_contact(tile, row offset, column offset, w_outlet, w_centre) in walk order. Fully unrolled: the window must stay
+// in registers, so every index is a compile-time constant.
+template <typename T, int C, bool FAST, typename F>
+WDPM_HD void wa_relax_pair_outlets(T (&w)[3][8], const T (&d)[3][8], F&& on_contact) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int tile = 0; tile < 2; tile++) {
+        const int c0 = C + 3 * tile;  // first column of the tile; the centre is (1, c0 + 1)
+        const T dc = d[1][c0 + 1];
+        T wc = w[1][c0 + 1];
+        const bool act = !is_outlet(dc) && (wc > T(0)) && is_valid_elevation(dc);
+        if (act) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+            for (int a = 0; a < 3; a++) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+                for (int b = 0; b < 3; b++) {
+                    if (a == 1 && b == 1) continue;
+                    const T dn = d[a][c0 + b];
+                    if (is_outlet(dn)) {
+                        on_contact(tile, a - 1, b - 1, w[a][c0 + b], wc);
+                        w[a][c0 + b] = T(0);
+                        wc = T(0);
+                    } else if (is_valid_elevation(dn)) {
+                        push_sel<T, kDrain, FAST>(dc, wc, dn, w[a][c0 + b]);
+                    }
+                }
+            }
+            w[1][c0 + 1] = wc;
+        }
+    }
+}
+
 }  // namespace wdpm

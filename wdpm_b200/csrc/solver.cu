@@ -19,9 +19,8 @@ namespace {
 
 constexpr int kDefaultVariantF64 = 17;  // warp-autonomous: 380-column window, two row triples per phase, 12 compute warps x 2 tiles per lane at 160 registers, Add fast step
 constexpr int kDefaultVariantF32 = 16;  // warp-autonomous: 752-column window, 24 compute warps x 2 tiles per lane
-constexpr int kDefaultVariantF32Drain = 12;  // k_fused: 484-column window (160 tiles = 5 whole warps per row group, named barriers), two CTAs of 15 compute warps per SM
-constexpr int kDefaultVariantF64DrainFast = 15;  // ... with the folded-gate Drain step (zero threshold > 0)
-constexpr int kDefaultVariantF64Drain = 14;  // Drain needs ~110 registers: 16 compute warps at 112 (register reallocation), 512 columns
+// round 1's production tilings of k_fused, still selectable by number (tests, comparisons): fp64 13 (Add / Subtract), 15 / 14 (Drain
+// with / without the folded-gate step), fp32 12
 // Grids of a few hundred thousand cells (the reference's basin5 is 482 x 471) cannot fill 148 SMs
 // with long chunks: narrow windows, two CTAs per SM and chunks of a few row triples spread the
 // rows over the whole chip in one wave (measured on basin5: 18 us per iteration against 37 us for
@@ -109,6 +108,12 @@ cudaError_t prepare_wa() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_fused_wa<T, kAdd, CFG, OPT | kOptNoGuard, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
+    if constexpr (!(OPT & kOptStagger)) {
+        e = cudaFuncSetAttribute(k_fused_wa<T, kDrain, CFG, OPT & ~kOptDrainFast, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_fused_wa<T, kDrain, CFG, OPT | kOptDrainFast, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+    }
     return cudaFuncSetAttribute(k_fused_wa<T, kSubtract, CFG, OPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
@@ -120,9 +125,16 @@ FusedVariant<T> make_wa_variant() {
     v.smem = wa_smem_bytes<CFG, T>();
     v.launch[kAdd] = launch_wa<T, kAdd, CFG, OPT, MINB>;
     v.launch[kSubtract] = launch_wa<T, kSubtract, CFG, OPT, MINB>;
-    v.launch[kDrain] = nullptr;
     v.launch_clean[kAdd] = (OPT & kOptAddFast) ? launch_wa<T, kAdd, CFG, OPT | kOptNoGuard, MINB> : nullptr;
-    v.launch_clean[kSubtract] = v.launch_clean[kDrain] = nullptr;
+    v.launch_clean[kSubtract] = nullptr;
+    // Drain: the reference form of the step, and - fp64, while the water is known to hold no -0.0 (water_clean) - the
+    // folded-gate form (relax.cuh, push_drain_fast). Not with the staggered schedule.
+    if constexpr (OPT & kOptStagger) {
+        v.launch[kDrain] = v.launch_clean[kDrain] = nullptr;
+    } else {
+        v.launch[kDrain] = launch_wa<T, kDrain, CFG, OPT & ~kOptDrainFast, MINB>;
+        v.launch_clean[kDrain] = sizeof(T) == 8 ? launch_wa<T, kDrain, CFG, OPT | kOptDrainFast, MINB> : nullptr;
+    }
     v.prepare = prepare_wa<T, CFG, OPT, MINB>;
     return v;
 }
@@ -761,10 +773,9 @@ int wdpm_create(const wdpm_config* cfg, wdpm_solver** out) {
     int variant = cfg->fused_variant;
     if (variant < 0 || variant > nvar) { delete s; return fail(WDPM_E_ARG, "fused_variant out of range"); }
     if (variant == 0) {
-        variant = s->dtype == WDPM_F64 ? (cfg->module == WDPM_DRAIN ? kDefaultVariantF64Drain : kDefaultVariantF64)
-                                       : (cfg->module == WDPM_DRAIN ? kDefaultVariantF32Drain : kDefaultVariantF32);
-        // Drain's folded-gate step needs water that is never -0.0: guaranteed by a zero threshold > 0 (relax.cuh)
-        if (s->dtype == WDPM_F64 && cfg->module == WDPM_DRAIN && cfg->zero_threshold > 0.0) variant = kDefaultVariantF64DrainFast;
+        // one kernel for the three modules (k_fused_wa); Drain's folded-gate step is chosen per launch, while the
+        // water is known to hold no -0.0 (wdpm_solver::water_clean), not here
+        variant = s->dtype == WDPM_F64 ? kDefaultVariantF64 : kDefaultVariantF32;
         if (cells < kSmallGridCells && !is_stripe) variant = s->dtype == WDPM_F64 ? kSmallGridVariantF64 : kSmallGridVariantF32;
         if (cfg->iters_per_launch > 1) {
             variant = 0;

@@ -19,9 +19,8 @@ KERNEL_AUTO, KERNEL_COLOUR, KERNEL_FUSED, KERNEL_RESIDENT = 0, 1, 2, 3
 MODULES = {"add": ADD, "subtract": SUBTRACT, "drain": DRAIN}
 # the tiling AUTO picks for large fp64 Add/Subtract grids (kDefaultVariantF64 in csrc/solver.cu); tests and
 # smoke() name it to exercise the production kernel on small grids
-PRODUCTION_FUSED_VARIANT_F64 = 17   # warp-autonomous kernel (k_fused_wa), Add / Subtract
+PRODUCTION_FUSED_VARIANT_F64 = 17   # warp-autonomous kernel (k_fused_wa), all three modules
 PRODUCTION_FUSED_VARIANT_F32 = 16
-PRODUCTION_FUSED_VARIANT_F64_DRAIN = 15  # k_fused with the folded-gate Drain step (zero threshold > 0)
 
 _PKG = Path(__file__).resolve().parent
 
