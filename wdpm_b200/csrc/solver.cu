@@ -1180,7 +1180,7 @@ int wdpm_copy_state(wdpm_solver* dst, wdpm_solver* src, int32_t what) {
     }
     CUDA_TRY(cudaStreamSynchronize(dst->stream));
     CUDA_TRY(cudaStreamSynchronize(src->stream));
-    return (what & WDPM_COPY_WATER) ? refresh_water_flags(dst) : WDPM_OK;
+    return refresh_water_flags(dst);  // a new DEM changes which cells are invalid, new water what they hold
 }
 
 int wdpm_get_cell_water(wdpm_solver* s, int32_t row, int32_t col, double* value) {
