@@ -186,6 +186,7 @@ class Solver:
 
     def set_outlet(self, drainrow: int, draincol: int):
         _check(self._lib.wdpm_set_outlet(self._h, C.c_int32(drainrow), C.c_int32(draincol)))
+        self.n_outlets = 1
 
     def set_outlets(self, outlets):
         """A set of outlet cells [(row, col), ...] in padded coordinates of the whole DEM (extension;
@@ -193,6 +194,7 @@ class Solver:
         rows = (C.c_int32 * len(outlets))(*[int(o[0]) for o in outlets])
         cols = (C.c_int32 * len(outlets))(*[int(o[1]) for o in outlets])
         _check(self._lib.wdpm_set_outlets(self._h, C.c_int32(len(outlets)), rows, cols))
+        self.n_outlets = len(outlets)
 
     def get_outlet_drains(self, n: int) -> np.ndarray:
         out = np.zeros(n, dtype=np.float64)

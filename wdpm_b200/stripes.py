@@ -140,7 +140,16 @@ class DistributedSolver:
         r = self.solver.run_block(n_iters)
         allr = [None] * self.world
         self.dist.all_gather_object(allr, r)
-        return combine_block_results(allr)
+        out = combine_block_results(allr)
+        n = getattr(self.solver, "n_outlets", 0)
+        if self.solver.module == _solver.DRAIN and n > 1:
+            # an outlet set: the single-solver total is the per-outlet totals added in outlet order, in the solver's
+            # precision (include/wdpm_b200.h); each total lives on one stripe, so gather them and add in that order
+            acc = self.solver.np_dtype(0)
+            for v in self.outlet_drains(n).astype(self.solver.np_dtype):
+                acc = self.solver.np_dtype(acc + v)
+            out.total_drain = float(acc)
+        return out
 
     def outlet_drains(self, n: int) -> np.ndarray:
         """Per-outlet totals of the whole DEM: each is kept by the stripe that owns the outlet's row (0 elsewhere),
